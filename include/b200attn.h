@@ -1,0 +1,152 @@
+/*
+ * b200attn.h -- C ABI of the B200-native paged-attention backend for mini-sglang.
+ *
+ * One shared library (libb200attn.so, built by mini-sglang_b200/build.py with
+ * `nvcc -gencode arch=compute_100a,code=sm_100a`), plain pointers and sizes, no torch
+ * types.  Every entry point enqueues work on the CUDA stream it is given and returns
+ * immediately (never synchronises, CUDA-graph capturable).  Device pointers unless noted.
+ *
+ * Return value: 0 = OK, non-zero = error; b200_last_error() returns a thread-local
+ * message.  The Python host turns a non-zero return into RuntimeError, mirroring the
+ * reference's PanicError -> RuntimeError convention
+ * (python/minisgl/kernel/csrc/include/minisgl/utils.h:40-88).
+ *
+ * Citations are path:line under the reference tree (M/ = python/minisgl/).
+ * dtype codes: 0 = bfloat16, 1 = float16 (elementwise/store ops); attention is bf16/fp16.
+ */
+#ifndef B200ATTN_H_
+#define B200ATTN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#define B200_DTYPE_BF16 0
+#define B200_DTYPE_FP16 1
+
+/* ABI version of this header (bumped on any signature change). */
+B200_API int b200_abi_version(void);
+/* Thread-local description of the last non-zero return. */
+B200_API const char* b200_last_error(void);
+/* Number of kernels this library has launched so far (bench.py's gpu_launches). */
+B200_API uint64_t b200_launch_count(void);
+/* 1 if the library was compiled for sm_100a and the current device is CC 10.x. */
+B200_API int b200_device_supported(void);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  KV append.  Replaces `store_cache(k_cache, v_cache, indices, k, v)`
+ *     (M/kernel/store.py:30-42 -> M/kernel/csrc/jit/store.cu:28-53,59-121), called from
+ *     MHAKVCache.store_kv (M/kvcache/mha_pool.py:45-56).
+ *     k_cache[indices[t]] = k[t]; v_cache[indices[t]] = v[t], rows of `row_bytes` bytes
+ *     (multiple of 16).  Strides in bytes.  indices int32 (idx64 = 0) or int64 (idx64 = 1).
+ * ------------------------------------------------------------------------------------- */
+B200_API int b200_store_kv(void* k_cache, void* v_cache, int64_t cache_row_stride_bytes,
+                  const void* k, const void* v, int64_t input_row_stride_bytes,
+                  const void* indices, int idx64, int64_t num_tokens, int64_t row_bytes,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K7  RMSNorm.  Replaces flashinfer.rmsnorm(x, w, eps, out=...) at M/layers/norm.py:16-21
+ *     and the per-head q/k norm at M/layers/attention.py:50-53.
+ *     x viewed as [rows, heads, dim]: element (r,h,i) at x + r*x_row_stride + h*x_head_stride + i
+ *     (strides in elements); plain 2-D input uses heads = 1.  out may alias x (in place).
+ *     y = float(x) * rsqrt(mean(x^2) + eps) * float(w), one rounding.  dim % 8 == 0, dim <= 16384.
+ * ------------------------------------------------------------------------------------- */
+B200_API int b200_rmsnorm(void* out, const void* x, const void* weight, int64_t rows, int heads, int dim,
+                 int64_t x_row_stride, int64_t x_head_stride, int64_t out_row_stride,
+                 int64_t out_head_stride, float eps, int dtype, void* stream);
+
+/* flashinfer.fused_add_rmsnorm(x, residual, w, eps) at M/layers/norm.py:32-38 (both in place):
+ * s = x + residual (fp32); residual <- round(s); x <- round(s * rsqrt(mean(s^2)+eps) * w). */
+B200_API int b200_fused_add_rmsnorm(void* x, void* residual, const void* weight, int64_t rows, int dim,
+                           int64_t x_row_stride, int64_t res_row_stride, float eps, int dtype,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K6  RoPE.  Replaces flashinfer.apply_rope_with_cos_sin_cache_inplace(positions, query, key,
+ *     head_size, cos_sin_cache) at M/layers/rotary.py:45-51: neox layout, fp32 cache
+ *     [max_pos, head_dim] = cos | sin, in place on q [nnz, hq, head_dim] / k [nnz, hkv, head_dim]
+ *     (row strides in elements, heads contiguous).  positions int32 (pos64=0) or int64.
+ * ------------------------------------------------------------------------------------- */
+B200_API int b200_rope_neox_inplace(void* q, void* k, const void* positions, int pos64,
+                           const float* cos_sin_cache, int64_t nnz, int hq, int hkv, int head_dim,
+                           int64_t q_row_stride, int64_t k_row_stride, int dtype, void* stream);
+
+/* Fused pre-attention: per-head q/k RMSNorm (weights may be NULL = skip) followed by neox
+ * RoPE, in place, one launch.  Replaces the three launches of AttentionLayer.forward
+ * (M/layers/attention.py:50-54). */
+B200_API int b200_qknorm_rope_inplace(void* q, void* k, const void* q_weight, const void* k_weight,
+                             float eps, const void* positions, int pos64,
+                             const float* cos_sin_cache, int64_t nnz, int hq, int hkv,
+                             int head_dim, int64_t q_row_stride, int64_t k_row_stride, int dtype,
+                             void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a2/a3/a4  Metadata on device.  Replaces the host loops of prepare_metadata
+ *     (M/attention/fa.py:67-105, fi.py:190-225): from per-request triples
+ *     req_info[bs][3] = (table_idx, cached_len, device_len) (int32, device) and the global
+ *     token-granular page table (M/core.py:103-104) produce
+ *       seq_lens[bs]            = device_len
+ *       cu_seqlens_q[bs+1]      = exclusive cumsum(device_len - cached_len)
+ *       cu_seqlens_k[bs+1]      = exclusive cumsum(device_len)
+ *       slot_table[bs][slot_table_stride] : row r = page_table[table_idx_r][0:width]
+ *       decode_plan[4 + bs + 1] : {chunk_tokens, total_chunks, bs, 0, chunk_start[bs+1]}
+ *         (split-KV work list for b200_attn_decode: request r owns chunks
+ *          [chunk_start[r], chunk_start[r+1]) of chunk_tokens tokens each).
+ *     width = number of table columns to copy (>= max device_len, <= both strides).
+ *     num_ctas_hint = persistent grid size the decode kernel will use (0 = default).
+ * ------------------------------------------------------------------------------------- */
+B200_API int b200_build_metadata(const int32_t* req_info, int bs, const int32_t* page_table,
+                        int64_t page_table_stride, int32_t* seq_lens, int32_t* cu_seqlens_q,
+                        int32_t* cu_seqlens_k, int32_t* slot_table, int64_t slot_table_stride,
+                        int width, int32_t* decode_plan, int num_kv_heads, int num_ctas_hint,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * a1  Attention forward.  Replace BaseAttnBackend.forward (M/attention/base.py:20-22; impls
+ *     fi.py:176-188, fa.py:49-65, trtllm.py:49-89): append k,v at out_loc, then causal
+ *     (bottom-right) softmax(q k^T * scale) v over each request's slots.
+ *     q   [nnz, hq, head_dim]  element (t,h,i) at q + t*q_row_stride + h*head_dim + i
+ *     k,v [nnz, hkv*head_dim]  row strides k_row_stride / v_row_stride (elements)
+ *     k_cache/v_cache: one layer of the pool viewed [slots, hkv, head_dim], contiguous rows
+ *       (M/kvcache/mha_pool.py:28-43); slot stride = hkv*head_dim elements.
+ *     slot_table [bs][slot_table_stride] int32 token-granular slots, seq_lens[bs] = kv length
+ *       INCLUDING the tokens appended by this call.
+ *     out [nnz, hq, head_dim] contiguous.  head_dim must be 128.
+ *     workspace: b200_attn_workspace_bytes(max_bs, hq) bytes, owned by the caller, may be
+ *       shared across layers (stream ordered).
+ * ------------------------------------------------------------------------------------- */
+B200_API size_t b200_attn_workspace_bytes(int max_bs, int hq, int head_dim);
+
+/* Decode: one query token per request (nnz == bs), KV append fused into the same launch. */
+B200_API int b200_attn_decode(const void* q, int64_t q_row_stride, const void* k, int64_t k_row_stride,
+                     const void* v, int64_t v_row_stride, void* k_cache, void* v_cache,
+                     const int32_t* out_loc, const int32_t* slot_table, int64_t slot_table_stride,
+                     const int32_t* seq_lens, const int32_t* decode_plan, int bs, int hq, int hkv,
+                     int head_dim, float scale, void* out, void* workspace, size_t workspace_bytes,
+                     int dtype, void* stream);
+
+/* Prefill / extend: ragged query rows, cu_seqlens_q[bs+1]; request r has
+ * q_len = cu_seqlens_q[r+1]-cu_seqlens_q[r] new tokens at kv positions
+ * [seq_lens[r]-q_len, seq_lens[r]).  max_seqlen_q is a host-side upper bound (grid sizing). */
+B200_API int b200_attn_prefill(const void* q, int64_t q_row_stride, const void* k, int64_t k_row_stride,
+                      const void* v, int64_t v_row_stride, void* k_cache, void* v_cache,
+                      const int32_t* out_loc, const int32_t* slot_table,
+                      int64_t slot_table_stride, const int32_t* seq_lens,
+                      const int32_t* cu_seqlens_q, int bs, int64_t nnz, int max_seqlen_q, int hq,
+                      int hkv, int head_dim, float scale, void* out, void* workspace,
+                      size_t workspace_bytes, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ATTN_H_ */

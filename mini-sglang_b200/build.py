@@ -1,0 +1,112 @@
+"""Build libb200attn.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+The library is pure CUDA runtime + C ABI (``include/b200attn.h``): no torch headers, so a
+rebuild takes seconds and the product .so travels to the GPU box with the snapshot.
+"""
+
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+from pathlib import Path
+from typing import List
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+INCLUDE = PKG_DIR.parent / "include"
+LIB_PATH = PKG_DIR / "libb200attn.so"
+STAMP = PKG_DIR / ".libb200attn.stamp"
+
+SOURCES = [
+    "capi.cu",
+    "elementwise.cu",
+    "metadata.cu",
+    "attn_decode.cu",
+    "attn_prefill.cu",
+]
+
+NVCC_FLAGS = [
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-O3",
+    "-std=c++17",
+    "-lineinfo",
+    "--expt-relaxed-constexpr",
+    "-Xcompiler",
+    "-fPIC",
+    "-Xcompiler",
+    "-fvisibility=hidden",
+    "-DB200_BUILDING=1",
+]
+
+
+def _nvcc() -> str:
+    cand = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
+    return cand if Path(cand).exists() else "nvcc"
+
+
+def _digest(sources: List[Path]) -> str:
+    h = hashlib.sha256()
+    for f in sorted(list(CSRC.glob("*.cu*")) + list(INCLUDE.glob("*.h"))):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(str(s.name) for s in sources).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every .cu under csrc/ into libb200attn.so (skips when sources are unchanged)."""
+    srcs = [CSRC / s for s in SOURCES]
+    for s in srcs:
+        if not s.exists():
+            raise FileNotFoundError(s)
+    digest = _digest(srcs)
+    if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text() == digest:
+        return LIB_PATH
+    objs = []
+    procs = []
+    build_dir = PKG_DIR / "build"
+    build_dir.mkdir(exist_ok=True)
+    for s in srcs:
+        o = build_dir / (s.stem + ".o")
+        cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(INCLUDE), "-I", str(CSRC), "-c", str(s), "-o", str(o)]
+        if verbose:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(o)
+    failed = False
+    for s, pr in procs:
+        out, _ = pr.communicate()
+        text = out.decode(errors="replace")
+        if pr.returncode != 0:
+            failed = True
+            sys.stderr.write(f"[b200 build] nvcc failed for {s.name}:\n{text}\n")
+        elif verbose or text.strip():
+            sys.stderr.write(f"[b200 build] {s.name}:\n{text}\n")
+    if failed:
+        raise RuntimeError("nvcc compilation failed (see stderr)")
+    link = [
+        _nvcc(),
+        "-shared",
+        "-gencode",
+        "arch=compute_100a,code=sm_100a",
+        "-o",
+        str(LIB_PATH),
+        *[str(o) for o in objs],
+        "-cudart",
+        "static",
+    ]
+    res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n" + res.stdout.decode(errors="replace"))
+    STAMP.write_text(digest)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

@@ -1,0 +1,35 @@
+// Library-level entry points of the C ABI (include/b200attn.h): error reporting, launch
+// accounting, device probe.  Errors follow the reference's convention of surfacing native
+// failures as Python RuntimeError (python/minisgl/kernel/csrc/include/minisgl/utils.h:40-88):
+// every entry point returns non-zero and leaves a message here.
+#include "b200attn.h"
+#include "common.cuh"
+
+#include <cstring>
+
+namespace b200 {
+
+static thread_local char t_error[512] = "";
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_error, sizeof(t_error), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace b200
+
+extern "C" int b200_abi_version(void) { return 1; }
+
+extern "C" const char* b200_last_error(void) { return b200::t_error; }
+
+extern "C" uint64_t b200_launch_count(void) { return b200::g_launch_count.load(); }
+
+extern "C" int b200_device_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}

@@ -1,0 +1,214 @@
+"""The layers that feed attention, with the reference's class and method names
+(``python/minisgl/layers/norm.py``, ``rotary.py``, ``attention.py``), bound to the sm_100a kernels.
+
+Two ways to use them:
+
+* stand-alone (tests, ``bench.py``): construct ``RMSNorm`` / ``RotaryEmbedding`` / ``AttentionLayer``
+  directly;
+* inside mini-sglang: :func:`patch_minisgl_layers` re-binds the kernel attributes the reference's
+  layer objects already hold (``RMSNorm.rmsnorm`` norm.py:14, ``RMSNormFused.{rmsnorm,
+  fused_add_rmsnorm}`` norm.py:29-30, ``RotaryEmbedding.apply_rope_with_cos_sin_cache_inplace``
+  rotary.py:35-37) -- zero edits to the reference.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Any, Callable, Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+from .core import get_global_ctx
+from .utils import div_even, get_tp_info
+
+
+class RMSNorm:
+    def __init__(self, size: int, eps: float) -> None:
+        self.eps = eps
+        self.weight = torch.empty(size)
+        self.rmsnorm = ops.rmsnorm
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.rmsnorm(x, self.weight, self.eps)
+
+    def forward_inplace(self, x: torch.Tensor) -> None:
+        self.rmsnorm(x, self.weight, self.eps, out=x)
+
+
+class RMSNormFused:
+    def __init__(self, size: int, eps: float) -> None:
+        self.eps = eps
+        self.weight = torch.empty(size)
+        self.rmsnorm = ops.rmsnorm
+        self.fused_add_rmsnorm = ops.fused_add_rmsnorm
+
+    def forward(
+        self, x: torch.Tensor, residual: Optional[torch.Tensor] = None
+    ) -> Tuple[torch.Tensor, torch.Tensor]:
+        if residual is None:
+            return self.rmsnorm(x, self.weight, self.eps), x
+        self.fused_add_rmsnorm(x, residual, self.weight, self.eps)
+        return x, residual
+
+
+def make_inv_freq(
+    rotary_dim: int, base: float, rope_scaling: Optional[Dict[str, Any]] = None
+) -> torch.Tensor:
+    """``base**(-2i/D)`` with the llama3 / yarn post-processing of rotary.py:55-114."""
+    inv_freq = 1.0 / (base ** (torch.arange(0, rotary_dim, 2, dtype=torch.float) / rotary_dim))
+    if rope_scaling is None or rope_scaling.get("rope_type", "default") == "default":
+        return inv_freq
+    kind = rope_scaling["rope_type"]
+    if kind == "llama3":
+        factor = rope_scaling["factor"]
+        lo, hi = rope_scaling["low_freq_factor"], rope_scaling["high_freq_factor"]
+        orig = rope_scaling["original_max_position_embeddings"]
+        wave_len = 2 * math.pi / inv_freq
+        if lo == hi:
+            return torch.where(wave_len < orig / hi, inv_freq, inv_freq / factor)
+        smooth = torch.clamp((orig / wave_len - lo) / (hi - lo), 0, 1)
+        return ((1 - smooth) / factor + smooth) * inv_freq
+    if kind == "yarn":
+        factor = rope_scaling["factor"]
+        beta_fast = rope_scaling.get("beta_fast", 32.0)
+        beta_slow = rope_scaling.get("beta_slow", 1.0)
+        orig = rope_scaling["original_max_position_embeddings"]
+
+        def corr(n_rot: float) -> float:
+            return rotary_dim * math.log(orig / (n_rot * 2 * math.pi)) / (2 * math.log(base))
+
+        low = max(math.floor(corr(beta_fast)), 0)
+        high = min(math.ceil(corr(beta_slow)), rotary_dim // 2 - 1)
+        ramp = torch.clamp(
+            (torch.arange(rotary_dim // 2, dtype=torch.float32) - low) / max(high - low, 1), 0, 1
+        )
+        return (inv_freq / factor) * ramp + inv_freq * (1 - ramp)
+    raise ValueError(f"Unsupported rope_scaling = {rope_scaling}")
+
+
+class RotaryEmbedding:
+    """fp32 ``[max_pos, D]`` cos|sin cache + in-place neox rotation (rotary.py:12-52)."""
+
+    def __init__(
+        self,
+        head_size: int,
+        rotary_dim: int,
+        max_position_embeddings: int,
+        base: float,
+        rope_scaling: Optional[Dict[str, Any]] = None,
+        device: Optional[torch.device] = None,
+    ) -> None:
+        if rotary_dim != head_size:
+            raise AssertionError("partial rotary is not supported (neither in the reference)")
+        if head_size not in (64, 128, 256):
+            raise AssertionError(f"head_size {head_size} not supported")
+        self.head_size = head_size
+        inv_freq = make_inv_freq(rotary_dim, base, rope_scaling)
+        t = torch.arange(max_position_embeddings, dtype=torch.float)
+        freqs = torch.einsum("i,j -> ij", t, inv_freq)
+        cache = torch.cat((freqs.cos(), freqs.sin()), dim=-1)
+        self._cos_sin_cache = cache.to(device) if device is not None else cache
+        self.apply_rope_with_cos_sin_cache_inplace = ops.apply_rope_with_cos_sin_cache_inplace
+
+    def forward(
+        self, positions: torch.Tensor, query: torch.Tensor, key: torch.Tensor
+    ) -> Tuple[torch.Tensor, torch.Tensor]:
+        self.apply_rope_with_cos_sin_cache_inplace(
+            positions=positions,
+            query=query,
+            key=key,
+            head_size=self.head_size,
+            cos_sin_cache=self._cos_sin_cache,
+        )
+        return query, key
+
+
+class AttentionLayer:
+    """split -> q/k norm -> RoPE -> ``ctx.attn_backend.forward`` (attention.py:18-57).
+
+    ``fuse_pre_attention=True`` runs the norm+RoPE sequence as the single fused launch
+    (``b200_qknorm_rope_inplace``); results are identical to the three-launch sequence.
+    """
+
+    def __init__(
+        self,
+        layer_id: int,
+        num_qo_heads: int,
+        num_kv_heads: int,
+        head_dim: int,
+        rotary: RotaryEmbedding,
+        q_norm: Optional[RMSNorm] = None,
+        k_norm: Optional[RMSNorm] = None,
+        fuse_pre_attention: bool = True,
+    ) -> None:
+        if num_qo_heads % num_kv_heads != 0:
+            raise AssertionError("num_qo_heads must be a multiple of num_kv_heads")
+        tp = get_tp_info().size
+        self.layer_id = layer_id
+        self.head_dim = head_dim
+        self.num_qo_heads = div_even(num_qo_heads, tp)
+        self.num_kv_heads = div_even(num_kv_heads, tp, allow_replicate=True)
+        self.qo_attn_dim = self.num_qo_heads * head_dim
+        self.kv_attn_dim = self.num_kv_heads * head_dim
+        self.rotary = rotary
+        self.q_norm = q_norm
+        self.k_norm = k_norm
+        self.fuse_pre_attention = fuse_pre_attention
+
+    def forward(self, qkv: torch.Tensor) -> torch.Tensor:
+        ctx = get_global_ctx()
+        q, k, v = qkv.split([self.qo_attn_dim, self.kv_attn_dim, self.kv_attn_dim], dim=-1)
+        if self.fuse_pre_attention:
+            eps = self.q_norm.eps if self.q_norm is not None else (
+                self.k_norm.eps if self.k_norm is not None else 0.0
+            )
+            ops.qknorm_rope_inplace(
+                ctx.batch.positions, q, k, self.head_dim, self.rotary._cos_sin_cache,
+                self.q_norm.weight if self.q_norm is not None else None,
+                self.k_norm.weight if self.k_norm is not None else None,
+                eps,
+            )
+        else:
+            if self.q_norm is not None:
+                self.q_norm.forward_inplace(q.view(-1, self.num_qo_heads, self.head_dim))
+            if self.k_norm is not None:
+                self.k_norm.forward_inplace(k.view(-1, self.num_kv_heads, self.head_dim))
+            q, k = self.rotary.forward(ctx.batch.positions, q, k)
+        q = q.view(-1, self.num_qo_heads, self.head_dim)
+        o = ctx.attn_backend.forward(q, k, v, self.layer_id, ctx.batch)
+        return o.view(-1, self.qo_attn_dim)
+
+
+def patch_minisgl_layers(model: Any) -> int:
+    """Re-bind the kernel attributes of every reference norm / rotary layer found under ``model``
+    (any object graph of ``BaseOP``s) to the sm_100a ops.  Returns the number of re-bound layers."""
+    seen, count = set(), 0
+    stack = [model]
+    while stack:
+        obj = stack.pop()
+        if id(obj) in seen or isinstance(obj, (torch.Tensor, str, bytes, int, float)):
+            continue
+        seen.add(id(obj))
+        hit = False
+        if callable(getattr(obj, "fused_add_rmsnorm", None)) and hasattr(obj, "weight"):
+            obj.fused_add_rmsnorm = ops.fused_add_rmsnorm
+            hit = True
+        if callable(getattr(obj, "rmsnorm", None)) and hasattr(obj, "weight"):
+            obj.rmsnorm = ops.rmsnorm
+            hit = True
+        if callable(getattr(obj, "apply_rope_with_cos_sin_cache_inplace", None)) and hasattr(
+            obj, "_cos_sin_cache"
+        ):
+            obj.apply_rope_with_cos_sin_cache_inplace = ops.apply_rope_with_cos_sin_cache_inplace
+            hit = True
+        count += int(hit)
+        children = []
+        if isinstance(obj, (list, tuple)):
+            children = list(obj)
+        elif isinstance(obj, dict):
+            children = list(obj.values())
+        elif hasattr(obj, "__dict__"):
+            children = [c for c in vars(obj).values() if not callable(c) or hasattr(c, "__dict__")]
+        stack.extend(children)
+    return count

