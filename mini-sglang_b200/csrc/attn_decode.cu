@@ -25,6 +25,8 @@ constexpr int kTile = 64;        // kv tokens per pipeline stage
 constexpr int kStages = 3;
 constexpr int kThreads = 128;
 constexpr int kRowBytes = kD * 2;  // 256 B per (token, head) row
+constexpr int kSlotRing = 4;       // slot-id prefetch ring (tiles)
+constexpr int kMaxBsSmem = 512;    // chunk_start / seq_lens are staged in smem up to this batch size
 
 template <typename T>
 struct DecodeParams {
@@ -70,13 +72,25 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
   float* sAlpha = sP + G * kTile;                       // [G]
   float* sL = sAlpha + 8;                               // [G]
   float* sM = sL + 8;                                   // [G]
+  int32_t* sSlot = reinterpret_cast<int32_t*>(sM + 8);  // [kSlotRing][kTile]
+  int32_t* sChunk = sSlot + kSlotRing * kTile;          // [kMaxBsSmem + 1]
+  int32_t* sSeq = sChunk + kMaxBsSmem + 1;              // [kMaxBsSmem]
 
   const int tid = threadIdx.x;
   const int lane = tid % kWarp, warp = tid / kWarp;
   const int chunk_tokens = p.plan[0];
   const int total_units = p.plan[1] * p.hkv;
-  const int32_t* chunk_start = p.plan + kPlanHeader;
-  const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+  const int32_t* chunk_start_g = p.plan + kPlanHeader;
+  const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV), sSlot_u = smem_u32(sSlot);
+  // per-request tables are read many times per CTA with dependent loads: stage them once
+  const bool staged = p.bs <= kMaxBsSmem;
+  if (staged) {
+    for (int i = tid; i <= p.bs; i += kThreads) sChunk[i] = chunk_start_g[i];
+    for (int i = tid; i < p.bs; i += kThreads) sSeq[i] = p.seq_lens[i];
+  }
+  __syncthreads();
+  const int32_t* chunk_start = staged ? sChunk : chunk_start_g;
+  const int32_t* seq_lens = staged ? sSeq : p.seq_lens;
 
   for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
     const int cg = unit / p.hkv;
@@ -90,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
     const int r = lo;
     const int c = cg - chunk_start[r];
     const int n_chunks = chunk_start[r + 1] - chunk_start[r];
-    const int kv_len = p.seq_lens[r];
+    const int kv_len = seq_lens[r];
     const int kv_begin = c * chunk_tokens;
     const int kv_end = min(kv_len, kv_begin + chunk_tokens);
     const int n_tiles = (kv_end - kv_begin + kTile - 1) / kTile;
@@ -124,10 +138,23 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
       sL[tid] = 0.f;
     }
 
+    // slot ids of tile t -> ring entry t % kSlotRing, asynchronously (joins the next commit group)
+    auto fetch_slots = [&](int t) {
+      if (t < n_tiles && tid < kTile) {
+        const int pos = kv_begin + t * kTile + tid;
+        if (pos < kv_end)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                           sSlot_u + (uint32_t)(((t % kSlotRing) * kTile + tid) * 4)),
+                       "l"(slots + pos)
+                       : "memory");
+      }
+    };
+    // K/V rows of tile t (slot ids must already be visible in the ring) + slot ids of tile t+2
     auto issue_tile = [&](int t) {
       if (t < n_tiles) {
         const int stage = t % kStages;
         const int tile_begin = kv_begin + t * kTile;
+        const int32_t* ring = sSlot + (t % kSlotRing) * kTile;
 #pragma unroll
         for (int i = 0; i < (kTile * 16) / kThreads; ++i) {
           const int idx = tid + i * kThreads;
@@ -141,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
               ksrc = k_new_row + cc * 8;
               vsrc = v_new_row + cc * 8;
             } else {
-              const int64_t off = (int64_t)slots[pos] * slot_stride + head_off + cc * 8;
+              const int64_t off = (int64_t)ring[row] * slot_stride + head_off + cc * 8;
               ksrc = p.k_cache + off;
               vsrc = p.v_cache + off;
             }
@@ -151,9 +178,15 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
           cp_async16_zfill(sV_u + o, vsrc, valid);
         }
       }
+      fetch_slots(t + 2);
       cp_async_commit();
     };
 
+    fetch_slots(0);
+    fetch_slots(1);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
 #pragma unroll
     for (int t = 0; t < kStages - 1; ++t) issue_tile(t);
 
@@ -291,7 +324,8 @@ __global__ void __launch_bounds__(kD) attn_combine_kernel(const float* __restric
 template <typename T, int G>
 static int launch_decode_g(const DecodeParams<T>& p, cudaStream_t st) {
   const size_t smem = 2 * kStages * kTile * kRowBytes +
-                      sizeof(float) * (G * kD + 2 * G * kTile + G * kTile + 24);
+                      sizeof(float) * (G * kD + 2 * G * kTile + G * kTile + 24) +
+                      sizeof(int32_t) * (kSlotRing * kTile + 2 * kMaxBsSmem + 1);
   static bool configured = false;
   if (!configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel<T, G>,

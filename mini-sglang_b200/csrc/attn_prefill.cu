@@ -19,6 +19,7 @@ constexpr int kBM = 64;   // q rows per CTA
 constexpr int kBN = 64;   // kv tokens per tile
 constexpr int kRowBytes = kD * 2;
 constexpr int kThreads = 128;
+constexpr int kSlotRing = 4;  // slot-id prefetch ring (tiles)
 
 template <typename T>
 struct PrefillParams {
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_prefill_kernel(const Prefill
   uint8_t* sQ = smem;                         // 64 x 256 B (reused as the output staging tile)
   uint8_t* sK = sQ + kBM * kRowBytes;         // 2 stages
   uint8_t* sV = sK + 2 * kBN * kRowBytes;     // 2 stages
+  int32_t* sSlot = reinterpret_cast<int32_t*>(sV + 2 * kBN * kRowBytes);  // [kSlotRing][kBN]
 
   const int r = blockIdx.z;
   const int head = blockIdx.y;
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_prefill_kernel(const Prefill
   const int32_t* slots = p.slot_table + (int64_t)r * p.st_stride;
   const int64_t slot_stride = (int64_t)p.hkv * kD;
   const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+  const uint32_t sSlot_u = smem_u32(sSlot);
 
   // keys visible to the last row of this q tile
   const int kv_hi = min(kv_len, cached + min(q_len, q_start + kBM));
@@ -121,10 +124,23 @@ __global__ void __launch_bounds__(kThreads, 2) attn_prefill_kernel(const Prefill
                          : p.q;
     cp_async16_zfill(sQ_u + swz(row, cc), src, valid);
   }
+  // slot ids of tile t -> ring entry t % kSlotRing (asynchronous; joins the next commit group)
+  auto fetch_slots = [&](int t) {
+    if (t < n_tiles && tid < kBN) {
+      const int pos = t * kBN + tid;
+      if (pos < kv_hi)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                         sSlot_u + (uint32_t)(((t % kSlotRing) * kBN + tid) * 4)),
+                     "l"(slots + pos)
+                     : "memory");
+    }
+  };
+  // K/V rows of tile t (its slot ids are already visible in the ring) + slot ids of tile t+2
   auto issue_tile = [&](int t) {
     if (t < n_tiles) {
       const int stage = t & 1;
       const int tile_begin = t * kBN;
+      const int32_t* ring = sSlot + (t % kSlotRing) * kBN;
 #pragma unroll
       for (int i = 0; i < (kBN * 16) / kThreads; ++i) {
         const int idx = tid + i * kThreads;
@@ -132,15 +148,21 @@ __global__ void __launch_bounds__(kThreads, 2) attn_prefill_kernel(const Prefill
         const int pos = tile_begin + row;
         const bool valid = pos < kv_hi;
         int64_t off = 0;
-        if (valid) off = (int64_t)slots[pos] * slot_stride + (int64_t)hk * kD + cc * 8;
+        if (valid) off = (int64_t)ring[row] * slot_stride + (int64_t)hk * kD + cc * 8;
         const uint32_t o = stage * (kBN * kRowBytes) + swz(row, cc);
         cp_async16_zfill(sK_u + o, p.k_cache + off, valid);
         cp_async16_zfill(sV_u + o, p.v_cache + off, valid);
       }
     }
+    fetch_slots(t + 2);
     cp_async_commit();
   };
-  issue_tile(0);  // group 0 = Q + tile 0
+  fetch_slots(0);
+  fetch_slots(1);
+  cp_async_commit();  // also carries the Q tile issued above
+  cp_async_wait<0>();
+  __syncthreads();
+  issue_tile(0);
 
   // ---- Q fragments (persistent): 8 k16-blocks x 4 regs
   uint32_t qf[8][4];
@@ -283,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_prefill_kernel(const Prefill
 
 template <typename T>
 static int launch_prefill(const PrefillParams<T>& p, int max_q, cudaStream_t st) {
-  const size_t smem = (kBM + 4 * kBN) * kRowBytes;  // 80 KB
+  const size_t smem = (kBM + 4 * kBN) * kRowBytes + kSlotRing * kBN * sizeof(int32_t);  // 81 KB
   static bool configured = false;
   if (!configured) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<T>,

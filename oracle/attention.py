@@ -36,15 +36,20 @@ def ref_attention_one(
     q_len, hq, d = q.shape
     kv_len, hkv, _ = k.shape
     g = hq // hkv
-    qf = q.float().permute(1, 0, 2)  # [Hq, q, D]
-    kf = k.float().permute(1, 0, 2).repeat_interleave(g, dim=0)  # [Hq, kv, D]
-    vf = v.float().permute(1, 0, 2).repeat_interleave(g, dim=0)
-    # bottom-right aligned causal mask
-    qi = torch.arange(q_len).unsqueeze(1) + (kv_len - q_len)
-    ki = torch.arange(kv_len).unsqueeze(0)
-    mask = ki <= qi  # [q, kv] True = attend
-    o = F.scaled_dot_product_attention(qf, kf, vf, attn_mask=mask, scale=scale)
-    return o.permute(1, 0, 2).contiguous()
+    # GQA without materialising repeated K/V: fold the group into the query-row axis,
+    # q -> [Hkv, g*q_len, D] against k, v -> [Hkv, kv_len, D]
+    qf = q.float().reshape(q_len, hkv, g, d).permute(1, 2, 0, 3).reshape(hkv, g * q_len, d)
+    kf = k.float().permute(1, 0, 2)  # [Hkv, kv, D]
+    vf = v.float().permute(1, 0, 2)
+    if q_len == 1:
+        mask = None  # the single (last) query row sees every key
+    else:
+        # bottom-right aligned causal mask, repeated for the g heads of a group
+        qi = torch.arange(q_len).unsqueeze(1) + (kv_len - q_len)
+        ki = torch.arange(kv_len).unsqueeze(0)
+        mask = (ki <= qi).repeat(g, 1)  # [g*q, kv] True = attend
+    o = F.scaled_dot_product_attention(qf, kf, vf, attn_mask=mask, scale=scale)  # [Hkv, g*q, D]
+    return o.reshape(hkv, g, q_len, d).permute(2, 0, 1, 3).reshape(q_len, hq, d).contiguous()
 
 
 def ref_paged_attention(

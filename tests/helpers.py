@@ -49,7 +49,8 @@ def make_world(
     shuffle_pages: bool = True,
 ) -> World:
     g = torch.Generator().manual_seed(seed)
-    max_seq_al = (max_seq + 31) // 32 * 32
+    al = max(64, page_size)
+    max_seq_al = (max_seq + al - 1) // al * al  # whole pages are written by the allocator
     if num_pages is None:
         num_pages = (max_reqs * max_seq_al) // page_size + 8
     slots = (num_pages + 1) * page_size  # +1 dummy page, like the engine
@@ -111,17 +112,23 @@ def oracle_forward(w: World, layer: int, q, k, v, md: o_meta.RefMetadata, fp32: 
 
 
 def attn_tolerance_ok(ours: torch.Tensor, ref32: torch.Tensor, what: str = ""):
-    """north_star tolerance: 1e-3 relative (to the tensor's magnitude) on the pre-rounding value,
-    plus the final rounding of the 16-bit output (half an ulp: 2^-9 bf16, 2^-12 fp16)."""
+    """Tolerance vs the exact-fp32 oracle.  north_star asks for 1e-3 relative against the
+    reference's FlashInfer path; that path (like ours) rounds the softmax probabilities P to the
+    16-bit type before the PV tensor-core product and rounds the output once more, so against an
+    *exact* oracle the budget per element is: 1e-3 * scale (arithmetic differences) + 1e-3 * scale
+    (P rounding, |dP/P| <= 2^-9, signs average out) + half an output ulp (<= 2^-8 |x| bf16,
+    2^-11 |x| fp16), with scale = max |ref|.  The relative Frobenius error is returned (and
+    bounded by 3e-3, bf16 rounding noise alone is ~1.6e-3)."""
     ours32 = ours.float().cpu()
     ulp = 2.0**-8 if ours.dtype == torch.bfloat16 else 2.0**-11
     scale = ref32.abs().max().item()
     err = (ours32 - ref32).abs()
-    bound = 1e-3 * scale + 0.5 * ulp * ref32.abs() + 1e-6
+    bound = 2e-3 * scale + ulp * ref32.abs() + 1e-6
     worst = (err - bound).max().item()
     rel_fro = (err.norm() / ref32.norm()).item()
     assert not torch.isnan(ours32).any(), f"{what}: NaN in output"
     assert worst <= 0, f"{what}: max violation {worst:.3e} (scale {scale:.3f}, rel_fro {rel_fro:.3e})"
+    assert rel_fro <= (3e-3 if ours.dtype == torch.bfloat16 else 1e-3), f"{what}: rel_fro {rel_fro:.3e}"
     return rel_fro
 
 

@@ -134,7 +134,7 @@ def test_prefill_radix_shared_prefix_pages(b200, native_lib):
     """Two requests whose leading page-table entries are identical (radix-shared pages)."""
     rel = _run_case(b200, page_size=16, hq=16, hkv=8, lens=[(0, 300), (128, 260), (128, 400)],
                     phase="prefill", share_prefix=0)
-    assert rel < 2e-3
+    assert rel < 3e-3
 
 
 def test_prefill_with_all_extend_len_one_uses_decode_kernel(b200, native_lib):

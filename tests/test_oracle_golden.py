@@ -1,0 +1,109 @@
+"""CPU: pin the oracle's integer functions against golden vectors produced by the reference's own
+Python code (tests/golden/make_metadata_golden.py), and cross-check the oracle's internals."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention as o_attn
+from oracle import metadata as o_meta
+from oracle import norm as o_norm
+from oracle import rope as o_rope
+from oracle.store import ref_store_kv, ref_store_kv_bytes
+
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "metadata_golden.json").read_text())
+
+
+@pytest.mark.parametrize("case", GOLDEN["cases"], ids=lambda c: c["name"])
+def test_metadata_oracle_matches_reference(case):
+    pt = np.array(case["page_table"], dtype=np.int32)
+    reqs = [tuple(r) for r in case["reqs"]]
+    ps = case["page_size"]
+    md = o_meta.ref_prepare_metadata(pt, reqs, ps)
+    assert md.positions.tolist() == case["positions"]
+    assert md.out_loc.tolist() == case["out_loc"]
+    assert md.cu_seqlens_q.tolist() == case["fa_cu_seqlens_q"] == case["fi_cu_seqlens_q"]
+    assert md.cu_seqlens_k.tolist() == case["fa_cu_seqlens_k"] == case["fi_cu_seqlens_k"]
+    assert md.cache_seqlens.tolist() == case["fa_cache_seqlens"] == case["fi_seq_lens"]
+    assert md.max_seqlen_q == case["fa_max_seqlen_q"] and md.max_seqlen_k == case["fa_max_seqlen_k"]
+    assert md.page_table_paged.tolist() == case["fa_page_table"]
+    assert md.indices_flat.tolist() == case["fi_indices"]
+    assert md.last_indices.tolist() == case["last_indices"] == case["fi_last_indices"]
+    for a in (md.cu_seqlens_q, md.cu_seqlens_k, md.cache_seqlens, md.out_loc, md.positions,
+              md.page_table_paged, md.indices_flat, md.slot_table, md.last_indices):
+        assert a.dtype == np.int32
+
+
+@pytest.mark.parametrize("case", GOLDEN["cases"], ids=lambda c: c["name"])
+def test_allocation_oracle_matches_reference(case):
+    """ref_allocate_paged reproduces the page table CacheManager.allocate_paged wrote."""
+    gold = np.array(case["page_table"], dtype=np.int32)
+    ps = case["page_size"]
+    table = np.zeros_like(gold)
+    table[-1, :] = gold[-1, 0]  # dummy row
+    free = list(case["free_slots_before"])
+    real = [tuple(r) for r in case["reqs"] if r[0] != gold.shape[0] - 1]
+    pre = [(t, 0, c) for (t, c, d) in real if c > 0]
+    o_meta.ref_allocate_paged(table, free, pre, ps)
+    o_meta.ref_allocate_paged(table, free, real, ps)
+    assert np.array_equal(table, gold)
+
+
+def test_store_oracle_is_a_byte_scatter():
+    torch.manual_seed(0)
+    kc = torch.randn(64, 2, 128).to(torch.bfloat16)
+    vc = torch.randn(64, 2, 128).to(torch.bfloat16)
+    qkv = torch.randn(9, 1024).to(torch.bfloat16)
+    k, v = qkv[:, 256:512], qkv[:, 512:768]
+    idx = torch.randperm(64)[:9].to(torch.int32)
+    kb = kc.view(64, -1).view(torch.uint8).numpy().copy()
+    ref_store_kv(kc, vc, idx, k, v)
+    want = ref_store_kv_bytes(kb, idx.numpy(), k.contiguous().view(torch.uint8).numpy())
+    assert np.array_equal(kc.view(64, -1).view(torch.uint8).numpy(), want)
+    assert torch.equal(vc[idx.long()].view(9, -1), v)
+
+
+def test_attention_oracle_against_naive_loops():
+    """SDPA restatement vs a literal per-element softmax (small case, pure loops)."""
+    torch.manual_seed(1)
+    q_len, kv_len, hq, hkv, d = 3, 7, 4, 2, 16
+    q = torch.randn(q_len, hq, d).to(torch.bfloat16)
+    k = torch.randn(kv_len, hkv, d).to(torch.bfloat16)
+    v = torch.randn(kv_len, hkv, d).to(torch.bfloat16)
+    out = o_attn.ref_attention_one(q, k, v, d**-0.5)
+    for i in range(q_len):
+        for h in range(hq):
+            hk = h // (hq // hkv)
+            lim = kv_len - q_len + i
+            s = torch.tensor([float(q[i, h].float() @ k[j, hk].float()) * d**-0.5 for j in range(lim + 1)])
+            p = torch.softmax(s, 0)
+            want = sum(p[j] * v[j, hk].float() for j in range(lim + 1))
+            assert torch.allclose(out[i, h], want, atol=1e-5, rtol=1e-5)
+
+
+def test_attention_flops_formula():
+    assert o_attn.attention_flops([1], [10], 2, 8) == 4 * 2 * 8 * (9 + 1)
+    assert o_attn.attention_flops([4], [4], 1, 1) == 4 * 10
+
+
+def test_rope_oracle_properties():
+    d = 128
+    cache = o_rope.ref_cos_sin_cache(d, 64, 1e6)
+    assert cache.shape == (64, d) and cache.dtype == torch.float32
+    x = torch.randn(5, 3 * d).to(torch.bfloat16)
+    same = o_rope.ref_apply_rope_neox(torch.zeros(5, dtype=torch.int32), x, d, cache)
+    assert torch.equal(same, x)  # position 0 is the identity
+    y = o_rope.ref_apply_rope_neox(torch.arange(5), x.float(), d, cache)
+    assert torch.allclose(y.reshape(5, 3, d).norm(dim=-1), x.float().reshape(5, 3, d).norm(dim=-1), rtol=1e-4)
+
+
+def test_norm_oracle_properties():
+    x = torch.randn(4, 256).to(torch.bfloat16)
+    w = torch.ones(256, dtype=torch.bfloat16)
+    y = o_norm.ref_rmsnorm(x, w, 0.0).float()
+    assert torch.allclose(y.pow(2).mean(-1), torch.ones(4), atol=2e-2)
+    nx, nr = o_norm.ref_fused_add_rmsnorm(x, x, w, 1e-6)
+    assert torch.equal(nr, (x.float() * 2).to(torch.bfloat16))
+    assert torch.allclose(nx.float(), o_norm.ref_rmsnorm((x.float() * 2), w.float(), 1e-6), atol=2e-2)

@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Kernel-level micro-benchmark on the bench workload (one decode iteration of cfg1, a few layers):
+used under ncu for the per-kernel captures in profiles/ and stand-alone for quick timing.
+
+    python tools/microbench.py decode --iter 500 --layers 4 --reps 5
+    python tools/microbench.py prefill --layers 2
+"""
+import argparse
+import importlib
+import sys
+from pathlib import Path
+from types import SimpleNamespace
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["decode", "prefill", "elementwise"])
+    ap.add_argument("--iter", type=int, default=500)
+    ap.add_argument("--layers", type=int, default=4)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--page-size", type=int, default=64)
+    ap.add_argument("--hq", type=int, default=bench.HQ)
+    ap.add_argument("--hkv", type=int, default=bench.HKV)
+    args = ap.parse_args()
+    bench.L = args.layers
+    bench.HQ, bench.HKV = args.hq, args.hkv
+    pkg = importlib.import_module("mini-sglang_b200")
+    pkg.build_native()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    sched = bench.Schedule()
+    r = bench.AttentionPathRunner(pkg, sched, args.hq, args.hkv, args.page_size, dev)
+    hq, hkv, D = r.hq, r.hkv, bench.D
+    peaks = bench.load_peaks()
+    with torch.cuda.stream(r.stream):
+        if args.what in ("decode", "elementwise"):
+            tr = sched.live(args.iter)
+            batch = r.make_batch(tr, "decode")
+            bs = batch.padded_size
+            pos_h, loc_h = r.host_inputs(batch)
+            batch.positions, batch.out_loc = pos_h.to(dev), loc_h.to(dev)
+            r.backend.prepare_metadata(batch)
+            qs = [r.qkv[l, :bs].split([hq * D, hkv * D, hkv * D], dim=-1) for l in range(args.layers)]
+            nbytes = bench.decode_bytes_per_layer([(x.table_idx, x.cached_len, x.device_len) for x in batch.padded_reqs], hq, hkv)
+            for rep in range(args.reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for l in range(args.layers):
+                    q, k, v = qs[l]
+                    if args.what == "elementwise":
+                        pkg.ops.qknorm_rope_inplace(batch.positions, q, k, D, r.rotary._cos_sin_cache, r.qw, r.kw, 1e-6)
+                    else:
+                        r.backend.forward(q.view(bs, hq, D), k, v, l, batch)
+                e1.record()
+                e1.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / args.layers
+                if args.what == "decode":
+                    print(f"decode bs={bs} sum_kv={sum(x[2] for x in tr)} : {us:.1f} us/layer, {nbytes / us / 1e3:.0f} GB/s "
+                          f"({nbytes / us / 1e3 / peaks['hbm_gbs']:.3f} of {peaks['source']} HBM peak) plan={batch.attn_metadata.decode_plan[:3].tolist()}")
+                else:
+                    eb = bs * (hq + hkv) * D * 2 * 2
+                    print(f"qknorm_rope bs={bs}: {us:.1f} us/layer, {eb / us / 1e3:.0f} GB/s")
+        else:
+            for tr in sched.prefill_batches()[:2]:
+                batch = r.make_batch(tr, "prefill")
+                pos_h, loc_h = r.host_inputs(batch)
+                nnz = pos_h.numel()
+                batch.positions, batch.out_loc = pos_h.to(dev), loc_h.to(dev)
+                r.backend.prepare_metadata(batch)
+                qkv = torch.randn((nnz, r.width), device=dev, dtype=torch.bfloat16)
+                q, k, v = qkv.split([hq * D, hkv * D, hkv * D], dim=-1)
+                for rep in range(args.reps):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for l in range(args.layers):
+                        r.backend.forward(q.view(nnz, hq, D), k, v, l, batch)
+                    e1.record()
+                    e1.synchronize()
+                    ms = e0.elapsed_time(e1) / args.layers
+                    fl = bench.prefill_flops_per_layer(tr, hq)
+                    print(f"prefill nnz={nnz} reqs={len(tr)}: {ms:.3f} ms/layer, {fl / ms / 1e9:.1f} TFLOP/s "
+                          f"({fl / ms / 1e9 / peaks['bf16_tflops']:.3f} of bf16 peak)")
+
+
+if __name__ == "__main__":
+    main()
