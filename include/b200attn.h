@@ -41,6 +41,10 @@ B200_API const char* b200_last_error(void);
 B200_API uint64_t b200_launch_count(void);
 /* 1 if the library was compiled for sm_100a and the current device is CC 10.x. */
 B200_API int b200_device_supported(void);
+/* Kernel selection knobs (debug / cross-checking only; defaults are the product path):
+ *   "decode_impl": 1 = tcgen05 + TMA-gather4 kernel (default), 0 = cp.async / CUDA-core kernel.
+ * Returns the previous value, or -1 for an unknown name. */
+B200_API int b200_set_option(const char* name, int value);
 
 /* ---------------------------------------------------------------------------------------
  * K1  KV append.  Replaces `store_cache(k_cache, v_cache, indices, k, v)`
@@ -117,8 +121,9 @@ B200_API int b200_build_metadata(const int32_t* req_info, int bs, const int32_t*
  *     (bottom-right) softmax(q k^T * scale) v over each request's slots.
  *     q   [nnz, hq, head_dim]  element (t,h,i) at q + t*q_row_stride + h*head_dim + i
  *     k,v [nnz, hkv*head_dim]  row strides k_row_stride / v_row_stride (elements)
- *     k_cache/v_cache: one layer of the pool viewed [slots, hkv, head_dim], contiguous rows
- *       (M/kvcache/mha_pool.py:28-43); slot stride = hkv*head_dim elements.
+ *     k_cache/v_cache: one layer of the pool viewed [num_slots, hkv, head_dim], contiguous rows
+ *       (M/kvcache/mha_pool.py:28-43); slot stride = hkv*head_dim elements; num_slots bounds the
+ *       TMA tensor map (rows >= num_slots read as zeros).
  *     slot_table [bs][slot_table_stride] int32 token-granular slots, seq_lens[bs] = kv length
  *       INCLUDING the tokens appended by this call.
  *     out [nnz, hq, head_dim] contiguous.  head_dim must be 128.
@@ -130,7 +135,7 @@ B200_API size_t b200_attn_workspace_bytes(int max_bs, int hq, int head_dim);
 /* Decode: one query token per request (nnz == bs), KV append fused into the same launch. */
 B200_API int b200_attn_decode(const void* q, int64_t q_row_stride, const void* k, int64_t k_row_stride,
                      const void* v, int64_t v_row_stride, void* k_cache, void* v_cache,
-                     const int32_t* out_loc, const int32_t* slot_table, int64_t slot_table_stride,
+                     int64_t num_slots, const int32_t* out_loc, const int32_t* slot_table, int64_t slot_table_stride,
                      const int32_t* seq_lens, const int32_t* decode_plan, int bs, int hq, int hkv,
                      int head_dim, float scale, void* out, void* workspace, size_t workspace_bytes,
                      int dtype, void* stream);
@@ -140,7 +145,7 @@ B200_API int b200_attn_decode(const void* q, int64_t q_row_stride, const void* k
  * [seq_lens[r]-q_len, seq_lens[r]).  max_seqlen_q is a host-side upper bound (grid sizing). */
 B200_API int b200_attn_prefill(const void* q, int64_t q_row_stride, const void* k, int64_t k_row_stride,
                       const void* v, int64_t v_row_stride, void* k_cache, void* v_cache,
-                      const int32_t* out_loc, const int32_t* slot_table,
+                      int64_t num_slots, const int32_t* out_loc, const int32_t* slot_table,
                       int64_t slot_table_stride, const int32_t* seq_lens,
                       const int32_t* cu_seqlens_q, int bs, int64_t nnz, int max_seqlen_q, int hq,
                       int hkv, int head_dim, float scale, void* out, void* workspace,

@@ -14,7 +14,7 @@ from typing import Optional
 _LIB: Optional[C.CDLL] = None
 LIB_PATH = Path(__file__).resolve().parent / "libb200attn.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _i32, _i64, _f32, _vp, _sz = C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
 
@@ -24,6 +24,7 @@ SIGNATURES = {
     "b200_last_error": (C.c_char_p, []),
     "b200_launch_count": (C.c_uint64, []),
     "b200_device_supported": (_i32, []),
+    "b200_set_option": (_i32, [C.c_char_p, _i32]),
     "b200_store_kv": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i32, _i64, _i64, _vp]),
     "b200_rmsnorm": (
         _i32,
@@ -45,12 +46,12 @@ SIGNATURES = {
     "b200_attn_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "b200_attn_decode": (
         _i32,
-        [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]
+        [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]
         + [_i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _i32, _vp],
     ),
     "b200_attn_prefill": (
         _i32,
-        [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]
+        [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp]
         + [_i32, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _i32, _vp],
     ),
 }
@@ -87,6 +88,14 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().b200_last_error().decode(errors="replace")
         raise B200NativeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def set_option(name: str, value: int) -> int:
+    """Debug knob, e.g. set_option("decode_impl", 0) selects the cp.async decode kernel."""
+    prev = load().b200_set_option(name.encode(), int(value))
+    if prev < 0:
+        raise B200NativeError(f"unknown option {name!r}")
+    return prev
 
 
 def launch_count() -> int:

@@ -24,6 +24,8 @@ SOURCES = [
     "elementwise.cu",
     "metadata.cu",
     "attn_decode.cu",
+    "attn_decode_tc.cu",
+    "tma_host.cu",
     "attn_prefill.cu",
 ]
 

@@ -15,11 +15,10 @@
 // from the k/v inputs.
 #include "b200attn.h"
 #include "common.cuh"
+#include "combine.cuh"
 
 namespace b200 {
 
-constexpr int kPlanHeader = 4;
-constexpr int kMaxSplits = 16;
 constexpr int kD = 128;          // head_dim
 constexpr int kTile = 64;        // kv tokens per pipeline stage
 constexpr int kStages = 3;
@@ -296,31 +295,6 @@ __global__ void __launch_bounds__(kThreads, 2) attn_decode_kernel(const DecodePa
   }
 }
 
-// ------------------------------------------------------------------------------- combine
-// grid (bs, hq), 128 threads (one per output dim). Requests with a single chunk were already
-// written by the attention kernel.
-template <typename T>
-__global__ void __launch_bounds__(kD) attn_combine_kernel(const float* __restrict__ part_o,
-                                                          const float* __restrict__ part_ml,
-                                                          const int32_t* __restrict__ plan, int hq,
-                                                          T* __restrict__ out) {
-  const int r = blockIdx.x, hh = blockIdx.y, d = threadIdx.x;
-  const int32_t* chunk_start = plan + kPlanHeader;
-  const int n = chunk_start[r + 1] - chunk_start[r];
-  if (n <= 1) return;
-  float m = -INFINITY;
-  for (int c = 0; c < n; ++c)
-    m = fmaxf(m, part_ml[(((int64_t)r * kMaxSplits + c) * hq + hh) * 2]);
-  float acc = 0.f, l = 0.f;
-  for (int c = 0; c < n; ++c) {
-    const int64_t idx = ((int64_t)r * kMaxSplits + c) * hq + hh;
-    const float w = fast_exp2(part_ml[idx * 2] - m);
-    l += w * part_ml[idx * 2 + 1];
-    acc += w * part_o[idx * kD + d];
-  }
-  out[((int64_t)r * hq + hh) * kD + d] = DTypeTraits<T>::from_float(acc / l);
-}
-
 template <typename T, int G>
 static int launch_decode_g(const DecodeParams<T>& p, cudaStream_t st) {
   const size_t smem = 2 * kStages * kTile * kRowBytes +
@@ -335,7 +309,7 @@ static int launch_decode_g(const DecodeParams<T>& p, cudaStream_t st) {
   const int grid = 2 * num_sms();
   attn_decode_kernel<T, G><<<grid, kThreads, smem, st>>>(p);
   B200_POST_LAUNCH();
-  attn_combine_kernel<T><<<dim3(p.bs, p.hq), kD, 0, st>>>(p.part_o, p.part_ml, p.plan, p.hq, p.out);
+  attn_combine_kernel<T><<<dim3(p.bs, p.hq), kHeadDim, 0, st>>>(p.part_o, p.part_ml, p.plan, p.hq, p.out);
   B200_POST_LAUNCH();
   return 0;
 }
@@ -366,9 +340,19 @@ extern "C" size_t b200_attn_workspace_bytes(int max_bs, int hq, int head_dim) {
   return items * head_dim * sizeof(float) + items * 2 * sizeof(float) + 256;
 }
 
+namespace b200 {
+extern std::atomic<int> g_decode_impl;
+int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, const void* v,
+                     int64_t v_rs, void* k_cache, void* v_cache, const int32_t* out_loc,
+                     const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
+                     const int32_t* plan, int bs, int hq, int hkv, int64_t num_slots, float scale_log2,
+                     void* out, float* part_o, float* part_ml, int dtype, cudaStream_t st);
+}  // namespace b200
+
 extern "C" int b200_attn_decode(const void* q, int64_t q_row_stride, const void* k,
                                 int64_t k_row_stride, const void* v, int64_t v_row_stride,
-                                void* k_cache, void* v_cache, const int32_t* out_loc,
+                                void* k_cache, void* v_cache, int64_t num_slots,
+                                const int32_t* out_loc,
                                 const int32_t* slot_table, int64_t slot_table_stride,
                                 const int32_t* seq_lens, const int32_t* decode_plan, int bs, int hq,
                                 int hkv, int head_dim, float scale, void* out, void* workspace,
@@ -391,6 +375,11 @@ extern "C" int b200_attn_decode(const void* q, int64_t q_row_stride, const void*
   float* part_o = reinterpret_cast<float*>(workspace);
   float* part_ml = part_o + items * kD;
   const float scale_log2 = scale * kLog2e;
+  B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "attn_decode: bad dtype %d", dtype);
+  if (g_decode_impl.load() == 1)
+    return launch_decode_tc(q, q_row_stride, k, k_row_stride, v, v_row_stride, k_cache, v_cache, out_loc,
+                            slot_table, slot_table_stride, seq_lens, decode_plan, bs, hq, hkv, num_slots,
+                            scale_log2, out, part_o, part_ml, dtype, st);
 #define FILL(T_)                                                                                  \
   DecodeParams<T_> p{(const T_*)q, q_row_stride, (const T_*)k, k_row_stride, (const T_*)v,        \
                      v_row_stride, (T_*)k_cache, (T_*)v_cache, out_loc, slot_table,               \

@@ -1,0 +1,501 @@
+// Blackwell-native batched decode: TMA gather4 -> swizzled smem -> tcgen05 UMMA (TMEM accumulators).
+//
+// Replaces store_kv + BatchDecodeWithPagedKVCacheWrapper.run (python/minisgl/attention/fi.py:185-188)
+// with one persistent launch (+ the split-KV combine).  HBM-bound; algorithmic bytes as in
+// attn_decode.cu.  One CTA per SM, 256 threads, warp-specialised:
+//
+//   warp 0   TMA producer: lane i owns key rows 4i..4i+3 of every 128-key tile; it reads their four
+//            token slots from the request's slot-table row (one 16-byte load) and issues four
+//            cp.async.bulk.tensor gather4 copies (K/V x two 64-column halves) that land directly
+//            in the 128-byte-swizzled layout UMMA consumes.  3-stage ring, 64 KB per stage.
+//   warp 1   UMMA issuer (one thread):  S^T[128 keys x 16] = K_tile[128 x 128] . Q^T   (K-major A, B)
+//                                       O^T[128 dims x 16] = V_tile^T[128 x 128 keys] . P^T (MN-major A)
+//            i.e. the keys / head dims fill the M = 128 dimension and the <= 8 query heads of the
+//            GQA group sit in N = 16, so no tensor-core row is wasted on padding and the score
+//            tile comes out with one key per TMEM lane = one key per softmax thread.
+//   warp 2   Q loader: the group's q rows -> swizzled smem operand (double buffered across units).
+//   warp 3   TMEM allocation (64 columns: 2 x S^T, 2 x O^T).
+//   warps 4-7 softmax + accumulation: thread i reads lane i of S^T (tcgen05.ld), the tile max is
+//            reduced with warp shuffles + one named barrier, P^T goes back to smem as the bf16 B
+//            operand, O^T tiles are read back and accumulated in registers with the online-softmax
+//            rescale; row sums are kept per thread and reduced once per unit.
+//
+// The token appended by this launch is handled without touching the pool copy that is being
+// written: its score / value come straight from the k/v inputs on CUDA cores in the epilogue of
+// the unit that owns position kv_len-1 (which also performs the append).
+#include "b200attn.h"
+#include "combine.cuh"
+#include "common.cuh"
+#include "sm100.cuh"
+
+#include <type_traits>
+
+namespace b200 {
+
+int get_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, bool is_bf16);
+
+namespace dtc {
+
+using namespace sm100;
+
+constexpr int kD = 128;
+constexpr int kTileN = 128;                 // keys per tile
+constexpr int kStages = 3;
+constexpr int kThreads = 256;
+constexpr int kHalfBytes = kTileN * 128;    // one 64-column half of a K or V tile: 16 KB
+constexpr int kStageBytes = 4 * kHalfBytes; // K h0 | K h1 | V h0 | V h1 = 64 KB
+constexpr int kQBufBytes = 2 * 2048;        // two halves of [16 rows x 128 B]
+constexpr int kPBufBytes = 16 * kTileN * 2; // P^T [16 x 128] bf16, no-swizzle K-major
+constexpr int kNPad = 16;                   // UMMA N (query heads of the group, padded)
+constexpr int kTmemCols = 64;               // S^T: 0,16  O^T: 32,48
+constexpr int kMaxBsSmem = 512;
+
+struct Smem {
+  // offsets from the 1024-aligned base
+  static constexpr int stages = 0;
+  static constexpr int qbuf = kStages * kStageBytes;
+  static constexpr int pbuf = qbuf + 2 * kQBufBytes;
+  static constexpr int bars = pbuf + 2 * kPBufBytes;      // 16 mbarriers
+  static constexpr int tmem_ptr = bars + 16 * 8;
+  static constexpr int red = tmem_ptr + 16;               // [2][4][16] floats (tile max), [4][16] (sums)
+  static constexpr int chunk = red + (2 * 4 * 16 + 4 * 16 + 4 * 16) * 4;
+  static constexpr int seq = chunk + (kMaxBsSmem + 1) * 4;
+  static constexpr int total = seq + kMaxBsSmem * 4;
+};
+enum Bar { kFull = 0, kEmpty = 3, kSFull = 6, kPFull = 8, kOFull = 10, kQFull = 12, kQEmpty = 14 };
+
+template <typename T>
+struct Params {
+  const T* q;
+  int64_t q_rs;
+  const T* k_new;
+  int64_t k_rs;
+  const T* v_new;
+  int64_t v_rs;
+  T* k_cache;
+  T* v_cache;
+  const int32_t* out_loc;
+  const int32_t* slot_table;
+  int64_t st_stride;
+  const int32_t* seq_lens;
+  const int32_t* plan;
+  int bs, hq, hkv;
+  int num_slots;
+  float scale_log2;
+  T* out;
+  float* part_o;
+  float* part_ml;
+};
+
+struct Unit {
+  int r, c, h, n_chunks, kv_len, kv_begin, kv_end_tc, n_tiles;
+  bool last_chunk;
+};
+
+__device__ __forceinline__ Unit get_unit(int unit, int hkv, int bs, int chunk_tokens,
+                                         const int32_t* chunk_start, const int32_t* seq_lens) {
+  Unit u;
+  const int cg = unit / hkv;
+  u.h = unit - cg * hkv;
+  int lo = 0, hi = bs;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (chunk_start[mid] <= cg) lo = mid; else hi = mid;
+  }
+  u.r = lo;
+  u.c = cg - chunk_start[lo];
+  u.n_chunks = chunk_start[lo + 1] - chunk_start[lo];
+  u.kv_len = seq_lens[lo];
+  u.kv_begin = u.c * chunk_tokens;
+  const int kv_end = min(u.kv_len, u.kv_begin + chunk_tokens);
+  u.last_chunk = (u.c == u.n_chunks - 1);
+  u.kv_end_tc = u.last_chunk ? kv_end - 1 : kv_end;  // the appended token is handled on CUDA cores
+  const int n = u.kv_end_tc - u.kv_begin;
+  u.n_tiles = n > 0 ? (n + kTileN - 1) / kTileN : 0;
+  return u;
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map_k,
+                      const __grid_constant__ CUtensorMap map_v) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B-swizzled tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid / kWarp, lane = tid % kWarp;
+  auto bar = [&](int i) { return sbase + Smem::bars + i * 8; };
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
+  float* red = reinterpret_cast<float*>(smem + Smem::red);
+  int32_t* sChunk = reinterpret_cast<int32_t*>(smem + Smem::chunk);
+  int32_t* sSeq = reinterpret_cast<int32_t*>(smem + Smem::seq);
+
+  const int chunk_tokens = p.plan[0];
+  const int total_units = p.plan[1] * p.hkv;
+  const int32_t* chunk_start_g = p.plan + kPlanHeader;
+  const bool staged = p.bs <= kMaxBsSmem;
+
+  // ---------------------------------------------------------------- one-time setup
+  if (staged) {
+    for (int i = tid; i <= p.bs; i += kThreads) sChunk[i] = chunk_start_g[i];
+    for (int i = tid; i < p.bs; i += kThreads) sSeq[i] = p.seq_lens[i];
+  }
+  // zero the operand buffers whose padding rows (heads >= G) are never written again
+  for (int i = tid; i < (2 * kQBufBytes + 2 * kPBufBytes) / 16; i += kThreads)
+    reinterpret_cast<uint4*>(smem + Smem::qbuf)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar(kFull + s), 1);
+      mbar_init(bar(kEmpty + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(kSFull + b), 1);
+      mbar_init(bar(kPFull + b), 128);
+      mbar_init(bar(kOFull + b), 1);
+      mbar_init(bar(kQFull + b), 1);
+      mbar_init(bar(kQEmpty + b), 1);
+    }
+    fence_barrier_init();
+    prefetch_tensormap(&map_k);
+    prefetch_tensormap(&map_v);
+  }
+  if (warp == 3) tmem_alloc(sbase + Smem::tmem_ptr, kTmemCols);
+  fence_proxy_async_smem();  // zero-fill above must be visible to UMMA operand reads
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const int32_t* chunk_start = staged ? sChunk : chunk_start_g;
+  const int32_t* seq_lens = staged ? sSeq : p.seq_lens;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer (32 lanes)
+    uint32_t tile_count = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
+      const int32_t* slots = p.slot_table + (int64_t)u.r * p.st_stride;
+      const int col0 = u.h * kD;
+      auto load_rows = [&](int t) {
+        int4 rr;
+        const int pos0 = u.kv_begin + t * kTileN + lane * 4;
+        if (pos0 + 3 < u.kv_end_tc) {
+          rr = __ldg(reinterpret_cast<const int4*>(slots + pos0));
+        } else {
+          rr.x = pos0 + 0 < u.kv_end_tc ? __ldg(slots + pos0 + 0) : p.num_slots;  // out of range row
+          rr.y = pos0 + 1 < u.kv_end_tc ? __ldg(slots + pos0 + 1) : p.num_slots;  //  => zero filled
+          rr.z = pos0 + 2 < u.kv_end_tc ? __ldg(slots + pos0 + 2) : p.num_slots;
+          rr.w = pos0 + 3 < u.kv_end_tc ? __ldg(slots + pos0 + 3) : p.num_slots;
+        }
+        return rr;
+      };
+      int4 nxt = make_int4(0, 0, 0, 0);
+      if (u.n_tiles > 0) nxt = load_rows(0);
+      for (int t = 0; t < u.n_tiles; ++t, ++tile_count) {
+        const int4 cur = nxt;
+        if (t + 1 < u.n_tiles) nxt = load_rows(t + 1);
+        const uint32_t stage = tile_count % kStages, phase = (tile_count / kStages) & 1;
+        mbar_wait(bar(kEmpty + stage), phase ^ 1);
+        if (lane == 0) mbar_arrive_expect_tx(bar(kFull + stage), kStageBytes);
+        __syncwarp();
+        const uint32_t dst = sbase + Smem::stages + stage * kStageBytes + lane * 512;
+        const uint32_t fb = bar(kFull + stage);
+        tma_gather4(dst + 0 * kHalfBytes, &map_k, fb, col0, cur.x, cur.y, cur.z, cur.w);
+        tma_gather4(dst + 1 * kHalfBytes, &map_k, fb, col0 + 64, cur.x, cur.y, cur.z, cur.w);
+        tma_gather4(dst + 2 * kHalfBytes, &map_v, fb, col0, cur.x, cur.y, cur.z, cur.w);
+        tma_gather4(dst + 3 * kHalfBytes, &map_v, fb, col0 + 64, cur.x, cur.y, cur.z, cur.w);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ UMMA issuer (one thread)
+    if (lane == 0) {
+      constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, kNPad, kBf16, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, kNPad, kBf16, true, false);
+      uint32_t tile_count = 0, unit_count = 0;
+      auto issue_qk = [&](uint32_t tc, uint32_t qb) {
+        const uint32_t stage = tc % kStages, phase = (tc / kStages) & 1;
+        mbar_wait(bar(kFull + stage), phase);
+        tc_fence_after_sync();
+        const uint32_t kb = sbase + Smem::stages + stage * kStageBytes;
+        const uint32_t qa = sbase + Smem::qbuf + qb * kQBufBytes;
+        const uint32_t d = tmem_base + (tc & 1) * kNPad;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = make_smem_desc(kb + (kk >> 2) * kHalfBytes + (kk & 3) * 32, 16, 1024, kLayoutSW128);
+          const uint64_t db = make_smem_desc(qa + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024, kLayoutSW128);
+          umma_f16_ss(d, da, db, idesc_qk, kk > 0);
+        }
+        umma_commit(bar(kSFull + (tc & 1)));
+      };
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
+        if (u.n_tiles == 0) continue;
+        const uint32_t qb = unit_count & 1;
+        mbar_wait(bar(kQFull + qb), (unit_count >> 1) & 1);
+        tc_fence_after_sync();
+        issue_qk(tile_count, qb);
+        if (u.n_tiles == 1) umma_commit(bar(kQEmpty + qb));
+        for (int j = 0; j < u.n_tiles; ++j) {
+          const uint32_t tc = tile_count + j;
+          if (j + 1 < u.n_tiles) {
+            issue_qk(tc + 1, qb);
+            if (j + 2 == u.n_tiles) umma_commit(bar(kQEmpty + qb));  // last QK of this unit issued
+          }
+          mbar_wait(bar(kPFull + (tc & 1)), (tc >> 1) & 1);
+          tc_fence_after_sync();
+          const uint32_t stage = tc % kStages;
+          const uint32_t vb = sbase + Smem::stages + stage * kStageBytes + 2 * kHalfBytes;
+          const uint32_t pb = sbase + Smem::pbuf + (tc & 1) * kPBufBytes;
+          const uint32_t d = tmem_base + 2 * kNPad + (tc & 1) * kNPad;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            // A = V^T (MN-major): 16 keys = two 8-key swizzle atoms of 1024 B; dims 64..127 at +16 KB
+            const uint64_t da = make_smem_desc(vb + kk * 2048, kHalfBytes, 1024, kLayoutSW128);
+            // B = P^T (K-major, no swizzle): 8x16-byte core matrices, k-chunks 128 B apart, n-groups 2 KB
+            const uint64_t db = make_smem_desc(pb + kk * 256, 128, 2048, kLayoutNone);
+            umma_f16_ss(d, da, db, idesc_pv, kk > 0);
+          }
+          umma_commit(bar(kOFull + (tc & 1)));
+          umma_commit(bar(kEmpty + stage));
+        }
+        tile_count += u.n_tiles;
+        ++unit_count;
+      }
+    }
+  } else if (warp == 2) {
+    // ============================================================ Q loader
+    uint32_t unit_count = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
+      if (u.n_tiles == 0) continue;
+      const uint32_t qb = unit_count & 1;
+      mbar_wait(bar(kQEmpty + qb), ((unit_count >> 1) & 1) ^ 1);
+      uint8_t* qdst = smem + Smem::qbuf + qb * kQBufBytes;
+      for (int idx = lane; idx < G * 16; idx += kWarp) {
+        const int g = idx >> 4, cc = idx & 15;
+        const Vec8 v = *reinterpret_cast<const Vec8*>(p.q + (int64_t)u.r * p.q_rs +
+                                                      (int64_t)(u.h * G + g) * kD + cc * 8);
+        *reinterpret_cast<Vec8*>(qdst + (cc >> 3) * 2048 + sw128_offset(g, cc & 7)) = v;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kQFull + qb));
+      ++unit_count;
+    }
+  } else if (warp >= 4) {
+    // ============================================================ softmax / accumulate (128 threads)
+    const int ct = tid - 128;          // 0..127 = TMEM lane = key within tile = output dim
+    const int cw = warp - 4;           // TMEM lane quadrant of this warp
+    const uint32_t lane_base = (uint32_t)(cw * 32) << 16;
+    float* red_max = red;              // [2][4][16]
+    float* red_sum = red + 2 * 4 * 16; // [4][16]
+    float* red_new = red_sum + 4 * 16; // [4][16]
+    uint32_t tile_count = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
+      float acc[G], l_thr[G], m_run[G], alpha_prev[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        acc[g] = 0.f;
+        l_thr[g] = 0.f;
+        m_run[g] = -INFINITY;
+        alpha_prev[g] = 0.f;
+      }
+      auto accumulate_o = [&](uint32_t tc) {
+        mbar_wait(bar(kOFull + (tc & 1)), (tc >> 1) & 1);
+        tc_fence_after_sync();
+        uint32_t o[16];
+        tmem_ld_x16(tmem_base + lane_base + 2 * kNPad + (tc & 1) * kNPad, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[g] = acc[g] * alpha_prev[g] + __uint_as_float(o[g]);
+      };
+      for (int j = 0; j < u.n_tiles; ++j) {
+        const uint32_t tc = tile_count + j;
+        mbar_wait(bar(kSFull + (tc & 1)), (tc >> 1) & 1);
+        tc_fence_after_sync();
+        uint32_t s[16];
+        tmem_ld_x16(tmem_base + lane_base + (tc & 1) * kNPad, s);
+        tmem_wait_ld();
+        const bool valid = u.kv_begin + j * kTileN + ct < u.kv_end_tc;
+        float sv[G];
+        float* rm = red_max + (tc & 1) * 64;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          sv[g] = valid ? __uint_as_float(s[g]) * p.scale_log2 : -INFINITY;
+          const float mx = warp_max(sv[g]);
+          if (lane == 0) rm[cw * 16 + g] = mx;
+        }
+        named_bar_sync(1, 128);
+        float alpha[G];
+        uint8_t* pdst = smem + Smem::pbuf + (tc & 1) * kPBufBytes;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float mt = fmaxf(fmaxf(rm[g], rm[16 + g]), fmaxf(rm[32 + g], rm[48 + g]));
+          const float m_new = fmaxf(m_run[g], mt);  // finite: every tile has >= 1 valid key
+          alpha[g] = fast_exp2(m_run[g] - m_new);
+          const float pv = fast_exp2(sv[g] - m_new);
+          l_thr[g] = l_thr[g] * alpha[g] + pv;
+          m_run[g] = m_new;
+          *reinterpret_cast<T*>(pdst + (g >> 3) * 2048 + (ct >> 3) * 128 + (g & 7) * 16 + (ct & 7) * 2) =
+              DTypeTraits<T>::from_float(pv);
+        }
+        fence_proxy_async_smem();   // P^T visible to the tensor core
+        tc_fence_before_sync();     // our tcgen05.ld of S^T is ordered before the next QK overwrite
+        mbar_arrive(bar(kPFull + (tc & 1)));
+        if (j > 0) accumulate_o(tc - 1);
+#pragma unroll
+        for (int g = 0; g < G; ++g) alpha_prev[g] = alpha[g];
+      }
+      if (u.n_tiles > 0) accumulate_o(tile_count + u.n_tiles - 1);
+      tile_count += u.n_tiles;
+
+      // ---- per-unit reductions on CUDA cores: row sums, and the appended token
+      float pnew[G];
+      {
+        const T* qrow = p.q + (int64_t)u.r * p.q_rs + (int64_t)(u.h * G) * kD + ct;
+        const float kn = u.last_chunk
+                             ? DTypeTraits<T>::to_float(p.k_new[(int64_t)u.r * p.k_rs + u.h * kD + ct])
+                             : 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float ls = warp_sum(l_thr[g]);
+          float sn = 0.f;
+          if (u.last_chunk) sn = warp_sum(DTypeTraits<T>::to_float(qrow[g * kD]) * kn);
+          if (lane == 0) {
+            red_sum[cw * 16 + g] = ls;
+            red_new[cw * 16 + g] = sn;
+          }
+        }
+        named_bar_sync(1, 128);
+      }
+      float l_tot[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        l_tot[g] = red_sum[g] + red_sum[16 + g] + red_sum[32 + g] + red_sum[48 + g];
+        pnew[g] = 0.f;
+      }
+      if (u.last_chunk) {
+        const float vn = DTypeTraits<T>::to_float(p.v_new[(int64_t)u.r * p.v_rs + u.h * kD + ct]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float s_new = (red_new[g] + red_new[16 + g] + red_new[32 + g] + red_new[48 + g]) * p.scale_log2;
+          const float m_new = fmaxf(m_run[g], s_new);
+          const float a = fast_exp2(m_run[g] - m_new);
+          pnew[g] = fast_exp2(s_new - m_new);
+          acc[g] = acc[g] * a + pnew[g] * vn;
+          l_tot[g] = l_tot[g] * a + pnew[g];
+          m_run[g] = m_new;
+        }
+        // fused KV append: copy this head's new K and V rows into the pool
+        if (ct < 32) {
+          const int64_t dst = (int64_t)p.out_loc[u.r] * p.hkv * kD + u.h * kD;
+          const int cc = ct & 15;
+          if (ct < 16) {
+            const Vec8 x = *reinterpret_cast<const Vec8*>(p.k_new + (int64_t)u.r * p.k_rs + u.h * kD + cc * 8);
+            *reinterpret_cast<Vec8*>(p.k_cache + dst + cc * 8) = x;
+          } else {
+            const Vec8 x = *reinterpret_cast<const Vec8*>(p.v_new + (int64_t)u.r * p.v_rs + u.h * kD + cc * 8);
+            *reinterpret_cast<Vec8*>(p.v_cache + dst + cc * 8) = x;
+          }
+        }
+      }
+      named_bar_sync(1, 128);  // red_sum / red_new are reused by the next unit
+      // ---- write out
+      if (u.n_chunks == 1) {
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          p.out[((int64_t)u.r * p.hq + u.h * G + g) * kD + ct] = DTypeTraits<T>::from_float(acc[g] / l_tot[g]);
+      } else {
+        const int64_t base = ((int64_t)u.r * kMaxSplits + u.c) * p.hq + u.h * G;
+#pragma unroll
+        for (int g = 0; g < G; ++g) p.part_o[(base + g) * kD + ct] = acc[g];
+        if (ct < G) {
+          // m_run / l_tot are uniform across threads; thread g stores head g's pair
+          float mm = 0.f, ll = 0.f;
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+            if (g == ct) {
+              mm = m_run[g];
+              ll = l_tot[g];
+            }
+          p.part_ml[(base + ct) * 2 + 0] = mm;
+          p.part_ml[(base + ct) * 2 + 1] = ll;
+        }
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <typename T, int G>
+static int launch_g(const Params<T>& p, const CUtensorMap& mk, const CUtensorMap& mv, cudaStream_t st) {
+  const size_t smem = Smem::total + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_tc_kernel<T, G>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  attn_decode_tc_kernel<T, G><<<num_sms(), kThreads, smem, st>>>(p, mk, mv);
+  B200_POST_LAUNCH();
+  attn_combine_kernel<T><<<dim3(p.bs, p.hq), kHeadDim, 0, st>>>(p.part_o, p.part_ml, p.plan, p.hq, p.out);
+  B200_POST_LAUNCH();
+  return 0;
+}
+
+template <typename T>
+static int launch(const Params<T>& p, cudaStream_t st) {
+  CUtensorMap mk, mv;
+  const bool bf16 = std::is_same<T, __nv_bfloat16>::value;
+  const uint64_t cols = (uint64_t)p.hkv * kD;
+  if (int rc = get_tensor_map_2d(&mk, p.k_cache, p.num_slots, cols, cols * 2, 64, 1, bf16)) return rc;
+  if (int rc = get_tensor_map_2d(&mv, p.v_cache, p.num_slots, cols, cols * 2, 64, 1, bf16)) return rc;
+  switch (p.hq / p.hkv) {
+    case 1: return launch_g<T, 1>(p, mk, mv, st);
+    case 2: return launch_g<T, 2>(p, mk, mv, st);
+    case 3: return launch_g<T, 3>(p, mk, mv, st);
+    case 4: return launch_g<T, 4>(p, mk, mv, st);
+    case 5: return launch_g<T, 5>(p, mk, mv, st);
+    case 6: return launch_g<T, 6>(p, mk, mv, st);
+    case 7: return launch_g<T, 7>(p, mk, mv, st);
+    case 8: return launch_g<T, 8>(p, mk, mv, st);
+    default:
+      set_error("attn_decode: GQA group size %d not supported (1..8)", p.hq / p.hkv);
+      return 1;
+  }
+}
+
+}  // namespace dtc
+
+// entry used by b200_attn_decode (attn_decode.cu)
+int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, const void* v,
+                     int64_t v_rs, void* k_cache, void* v_cache, const int32_t* out_loc,
+                     const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
+                     const int32_t* plan, int bs, int hq, int hkv, int64_t num_slots, float scale_log2,
+                     void* out, float* part_o, float* part_ml, int dtype, cudaStream_t st) {
+  B200_CHECK_ARG(num_slots > 0 && num_slots < (1ll << 31), "attn_decode: bad num_slots %lld",
+                 (long long)num_slots);
+  B200_CHECK_ARG(st_stride % 4 == 0 && ((uintptr_t)slot_table % 16) == 0,
+                 "attn_decode: slot table rows must be 16-byte aligned");
+#define RUN(T_)                                                                                   \
+  dtc::Params<T_> p{(const T_*)q, q_rs, (const T_*)k, k_rs, (const T_*)v, v_rs, (T_*)k_cache,     \
+                    (T_*)v_cache, out_loc, slot_table, st_stride, seq_lens, plan, bs, hq, hkv,    \
+                    (int)num_slots, scale_log2, (T_*)out, part_o, part_ml};                       \
+  return dtc::launch<T_>(p, st)
+  if (dtype == B200_DTYPE_BF16) {
+    RUN(__nv_bfloat16);
+  }
+  RUN(__half);
+#undef RUN
+}
+
+}  // namespace b200

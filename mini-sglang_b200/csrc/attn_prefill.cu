@@ -324,13 +324,15 @@ using namespace b200;
 
 extern "C" int b200_attn_prefill(const void* q, int64_t q_row_stride, const void* k,
                                  int64_t k_row_stride, const void* v, int64_t v_row_stride,
-                                 void* k_cache, void* v_cache, const int32_t* out_loc,
-                                 const int32_t* slot_table, int64_t slot_table_stride,
+                                 void* k_cache, void* v_cache, int64_t num_slots,
+                                 const int32_t* out_loc, const int32_t* slot_table,
+                                 int64_t slot_table_stride,
                                  const int32_t* seq_lens, const int32_t* cu_seqlens_q, int bs,
                                  int64_t nnz, int max_seqlen_q, int hq, int hkv, int head_dim,
                                  float scale, void* out, void* workspace, size_t workspace_bytes,
                                  int dtype, void* stream) {
   (void)workspace;
+  (void)num_slots;
   (void)workspace_bytes;
   B200_CHECK_ARG(head_dim == kD, "attn_prefill: head_dim must be 128 (got %d)", head_dim);
   B200_CHECK_ARG(bs > 0 && hq > 0 && hkv > 0 && hq % hkv == 0,

@@ -12,6 +12,15 @@ from oracle import metadata as o_meta
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[1, 0], ids=["tcgen05", "cpasync"])
+def decode_impl(request, b200, native_lib):
+    """Both decode kernels are held to the same oracle: the tcgen05 + TMA-gather4 product kernel
+    and the cp.async / CUDA-core bring-up kernel (selected with the debug option)."""
+    prev = b200._cabi.set_option("decode_impl", request.param)
+    yield request.param
+    b200._cabi.set_option("decode_impl", prev)
+
+
 def _check_metadata(md, ref: o_meta.RefMetadata, page_size: int):
     bs = len(ref.cache_seqlens)
     assert np.array_equal(md.cache_seqlens.cpu().numpy(), ref.cache_seqlens)
@@ -84,26 +93,26 @@ DECODE_LENS = {
 
 @pytest.mark.parametrize("page_size", [1, 16, 64])
 @pytest.mark.parametrize("name", list(DECODE_LENS))
-def test_decode_qwen3_0p6b_shape(b200, native_lib, page_size, name):
+def test_decode_qwen3_0p6b_shape(b200, native_lib, page_size, name, decode_impl):
     _run_case(b200, page_size=page_size, hq=16, hkv=8, lens=DECODE_LENS[name], phase="decode")
 
 
 @pytest.mark.parametrize("hq,hkv", [(8, 8), (40, 8), (64, 8), (8, 1), (4, 2), (16, 2), (7, 1), (6, 2), (3, 1)])
-def test_decode_gqa_groups(b200, native_lib, hq, hkv):
+def test_decode_gqa_groups(b200, native_lib, hq, hkv, decode_impl):
     """Hq/Hkv of every BASELINE model at tp 1/2/4/8 (GQA 1,2,5,8) plus odd group sizes."""
     _run_case(b200, page_size=16, hq=hq, hkv=hkv, lens=DECODE_LENS["mixed"][:5], phase="decode")
 
 
-def test_decode_padded_dummy_requests(b200, native_lib):
+def test_decode_padded_dummy_requests(b200, native_lib, decode_impl):
     """Graph-padded batch: dummy requests (kv_len 1, shared dummy slot) ride along (graph.py:160-166)."""
     _run_case(b200, page_size=16, hq=16, hkv=8, lens=DECODE_LENS["mixed"][:3], phase="decode", pad_to=8)
 
 
-def test_decode_fp16(b200, native_lib):
+def test_decode_fp16(b200, native_lib, decode_impl):
     _run_case(b200, page_size=1, hq=16, hkv=8, lens=DECODE_LENS["mixed"][:4], phase="decode", dtype=torch.float16)
 
 
-def test_decode_second_layer_of_pool(b200, native_lib):
+def test_decode_second_layer_of_pool(b200, native_lib, decode_impl):
     _run_case(b200, page_size=16, hq=16, hkv=8, lens=DECODE_LENS["tiny"], phase="decode", layer=2, layers=3)
 
 
@@ -137,7 +146,7 @@ def test_prefill_radix_shared_prefix_pages(b200, native_lib):
     assert rel < 3e-3
 
 
-def test_prefill_with_all_extend_len_one_uses_decode_kernel(b200, native_lib):
+def test_prefill_with_all_extend_len_one_uses_decode_kernel(b200, native_lib, decode_impl):
     _run_case(b200, page_size=16, hq=16, hkv=8, lens=[(16, 17), (32, 33)], phase="prefill")
 
 
@@ -151,7 +160,7 @@ def test_forward_rejects_cpu_and_foreign_metadata(b200, native_lib):
         gw.backend.forward(q, q.view(1, -1)[:, :1024], q.view(1, -1)[:, :1024], 0, batch)
 
 
-def test_cuda_graph_capture_and_replay(b200, native_lib):
+def test_cuda_graph_capture_and_replay(b200, native_lib, decode_impl):
     """init_capture_graph / prepare_for_capture / prepare_for_replay drive a captured decode
     (reference engine/graph.py:105-158): replayed output == eager output, pool rows appended."""
     hq, hkv, d, ps = 16, 8, 128, 16
@@ -208,7 +217,7 @@ def test_cuda_graph_capture_and_replay(b200, native_lib):
     assert torch.equal(kc[slots].view(torch.int16), ref_kc[slots].view(torch.int16))
 
 
-def test_decode_full_size_properties(b200, native_lib):
+def test_decode_full_size_properties(b200, native_lib, decode_impl):
     """BASELINE cfg1 decode shape (256 seqs, Qwen3-0.6B heads, lens U[100,2048]) -- too big for
     the CPU oracle in seconds, so size-independent properties: (a) appended rows bit-exact,
     (b) a sample of requests matches the oracle, (c) invariance to the split-KV chunking,
