@@ -124,6 +124,9 @@ B200_API int b200_build_metadata(const int32_t* req_info, int bs, const int32_t*
  *     k_cache/v_cache: one layer of the pool viewed [num_slots, hkv, head_dim], contiguous rows
  *       (M/kvcache/mha_pool.py:28-43); slot stride = hkv*head_dim elements; num_slots bounds the
  *       TMA tensor map (rows >= num_slots read as zeros).
+ *     page_size: allocation granularity behind the slot table (Context.page_size, M/core.py:103):
+ *       the slots of positions [j*page_size, (j+1)*page_size) of a request are consecutive
+ *       (M/scheduler/cache.py:119-146).  1 = no contiguity is assumed.
  *     slot_table [bs][slot_table_stride] int32 token-granular slots, seq_lens[bs] = kv length
  *       INCLUDING the tokens appended by this call.
  *     out [nnz, hq, head_dim] contiguous.  head_dim must be 128.
@@ -135,7 +138,7 @@ B200_API size_t b200_attn_workspace_bytes(int max_bs, int hq, int head_dim);
 /* Decode: one query token per request (nnz == bs), KV append fused into the same launch. */
 B200_API int b200_attn_decode(const void* q, int64_t q_row_stride, const void* k, int64_t k_row_stride,
                      const void* v, int64_t v_row_stride, void* k_cache, void* v_cache,
-                     int64_t num_slots, const int32_t* out_loc, const int32_t* slot_table, int64_t slot_table_stride,
+                     int64_t num_slots, int page_size, const int32_t* out_loc, const int32_t* slot_table, int64_t slot_table_stride,
                      const int32_t* seq_lens, const int32_t* decode_plan, int bs, int hq, int hkv,
                      int head_dim, float scale, void* out, void* workspace, size_t workspace_bytes,
                      int dtype, void* stream);
@@ -145,7 +148,7 @@ B200_API int b200_attn_decode(const void* q, int64_t q_row_stride, const void* k
  * [seq_lens[r]-q_len, seq_lens[r]).  max_seqlen_q is a host-side upper bound (grid sizing). */
 B200_API int b200_attn_prefill(const void* q, int64_t q_row_stride, const void* k, int64_t k_row_stride,
                       const void* v, int64_t v_row_stride, void* k_cache, void* v_cache,
-                      int64_t num_slots, const int32_t* out_loc, const int32_t* slot_table,
+                      int64_t num_slots, int page_size, const int32_t* out_loc, const int32_t* slot_table,
                       int64_t slot_table_stride, const int32_t* seq_lens,
                       const int32_t* cu_seqlens_q, int bs, int64_t nnz, int max_seqlen_q, int hq,
                       int hkv, int head_dim, float scale, void* out, void* workspace,

@@ -213,7 +213,8 @@ class B200AttnBackend(BaseAttnBackend):
             _cabi.check(
                 self._lib.b200_attn_decode(
                     q3.data_ptr(), q3.stride(0), k2.data_ptr(), k2.stride(0), v2.data_ptr(),
-                    v2.stride(0), kc.data_ptr(), vc.data_ptr(), num_slots, out_loc.data_ptr(),
+                    v2.stride(0), kc.data_ptr(), vc.data_ptr(), num_slots, self.page_size,
+                    out_loc.data_ptr(),
                     md.page_table.data_ptr(), md.page_table.stride(0), md.cache_seqlens.data_ptr(),
                     md.decode_plan.data_ptr(), md.bs, hq, hkv, d, self.scale, out.data_ptr(),
                     ws.data_ptr(), ws.numel(), dtype, stream,
@@ -224,7 +225,8 @@ class B200AttnBackend(BaseAttnBackend):
             _cabi.check(
                 self._lib.b200_attn_prefill(
                     q3.data_ptr(), q3.stride(0), k2.data_ptr(), k2.stride(0), v2.data_ptr(),
-                    v2.stride(0), kc.data_ptr(), vc.data_ptr(), num_slots, out_loc.data_ptr(),
+                    v2.stride(0), kc.data_ptr(), vc.data_ptr(), num_slots, self.page_size,
+                    out_loc.data_ptr(),
                     md.page_table.data_ptr(), md.page_table.stride(0), md.cache_seqlens.data_ptr(),
                     md.cu_seqlens_q.data_ptr(), md.bs, nnz, md.max_seqlen_q, hq, hkv, d, self.scale,
                     out.data_ptr(), ws.data_ptr(), ws.numel(), dtype, stream,

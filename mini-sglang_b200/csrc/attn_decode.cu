@@ -345,13 +345,14 @@ extern std::atomic<int> g_decode_impl;
 int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, const void* v,
                      int64_t v_rs, void* k_cache, void* v_cache, const int32_t* out_loc,
                      const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
-                     const int32_t* plan, int bs, int hq, int hkv, int64_t num_slots, float scale_log2,
-                     void* out, float* part_o, float* part_ml, int dtype, cudaStream_t st);
+                     const int32_t* plan, int bs, int hq, int hkv, int64_t num_slots, int page_size,
+                     float scale_log2, void* out, float* part_o, float* part_ml, int dtype,
+                     cudaStream_t st);
 }  // namespace b200
 
 extern "C" int b200_attn_decode(const void* q, int64_t q_row_stride, const void* k,
                                 int64_t k_row_stride, const void* v, int64_t v_row_stride,
-                                void* k_cache, void* v_cache, int64_t num_slots,
+                                void* k_cache, void* v_cache, int64_t num_slots, int page_size,
                                 const int32_t* out_loc,
                                 const int32_t* slot_table, int64_t slot_table_stride,
                                 const int32_t* seq_lens, const int32_t* decode_plan, int bs, int hq,
@@ -370,6 +371,7 @@ extern "C" int b200_attn_decode(const void* q, int64_t q_row_stride, const void*
                  "attn_decode: workspace too small (%zu < %zu)", workspace_bytes,
                  b200_attn_workspace_bytes(bs, hq, head_dim));
   B200_CHECK_ARG(decode_plan != nullptr, "attn_decode: decode_plan is NULL (b200_build_metadata)");
+  B200_CHECK_ARG(page_size >= 1, "attn_decode: page_size must be >= 1");
   auto st = (cudaStream_t)stream;
   const size_t items = (size_t)bs * kMaxSplits * hq;
   float* part_o = reinterpret_cast<float*>(workspace);
@@ -379,7 +381,7 @@ extern "C" int b200_attn_decode(const void* q, int64_t q_row_stride, const void*
   if (g_decode_impl.load() == 1)
     return launch_decode_tc(q, q_row_stride, k, k_row_stride, v, v_row_stride, k_cache, v_cache, out_loc,
                             slot_table, slot_table_stride, seq_lens, decode_plan, bs, hq, hkv, num_slots,
-                            scale_log2, out, part_o, part_ml, dtype, st);
+                            page_size, scale_log2, out, part_o, part_ml, dtype, st);
 #define FILL(T_)                                                                                  \
   DecodeParams<T_> p{(const T_*)q, q_row_stride, (const T_*)k, k_row_stride, (const T_*)v,        \
                      v_row_stride, (T_*)k_cache, (T_*)v_cache, out_loc, slot_table,               \

@@ -2,19 +2,24 @@
 //
 // Replaces store_kv + BatchDecodeWithPagedKVCacheWrapper.run (python/minisgl/attention/fi.py:185-188)
 // with one persistent launch (+ the split-KV combine).  HBM-bound; algorithmic bytes as in
-// attn_decode.cu.  One CTA per SM, 256 threads, warp-specialised:
+// attn_decode.cu.  One CTA per SM, 384 threads, warp-specialised:
 //
-//   warp 0   TMA producer: lane i owns key rows 4i..4i+3 of every 128-key tile; it reads their four
-//            token slots from the request's slot-table row (one 16-byte load) and issues four
-//            cp.async.bulk.tensor gather4 copies (K/V x two 64-column halves) that land directly
-//            in the 128-byte-swizzled layout UMMA consumes.  3-stage ring, 64 KB per stage.
-//   warp 1   UMMA issuer (one thread):  S^T[128 keys x 16] = K_tile[128 x 128] . Q^T   (K-major A, B)
+//   warps 0-3 TMA producers, 3-stage ring of 64 KB stages (K/V x two 64-column halves of a 128-key
+//            tile), data lands directly in the 128-byte-swizzled layout UMMA consumes.
+//            * page_size >= 8 ("box mode", warp 0 only): the slots of a page are contiguous rows of
+//              the pool, so one tiled TMA box of min(page_size, 64) rows x 128 B is issued per page
+//              piece -- 8 instructions per tile at page_size 64.  The one box of a request that
+//              straddles the end of its KV range falls back to gather4 with out-of-range rows
+//              (zero filled), so stale pool memory is never multiplied in.
+//            * page_size < 8 ("gather mode", all four warps): cp.async.bulk.tensor ...gather4, four
+//              arbitrary token rows per instruction, one instruction per lane per tile.
+//   warp 8   UMMA issuer (one thread):  S^T[128 keys x 16] = K_tile[128 x 128] . Q^T   (K-major A, B)
 //                                       O^T[128 dims x 16] = V_tile^T[128 x 128 keys] . P^T (MN-major A)
 //            i.e. the keys / head dims fill the M = 128 dimension and the <= 8 query heads of the
 //            GQA group sit in N = 16, so no tensor-core row is wasted on padding and the score
 //            tile comes out with one key per TMEM lane = one key per softmax thread.
-//   warp 2   Q loader: the group's q rows -> swizzled smem operand (double buffered across units).
-//   warp 3   TMEM allocation (64 columns: 2 x S^T, 2 x O^T).
+//   warp 9   Q loader: the group's q rows -> swizzled smem operand (double buffered across units);
+//            also owns the TMEM allocation (64 columns: 2 x S^T, 2 x O^T).
 //   warps 4-7 softmax + accumulation: thread i reads lane i of S^T (tcgen05.ld), the tile max is
 //            reduced with warp shuffles + one named barrier, P^T goes back to smem as the bf16 B
 //            operand, O^T tiles are read back and accumulated in registers with the online-softmax
@@ -42,7 +47,8 @@ using namespace sm100;
 constexpr int kD = 128;
 constexpr int kTileN = 128;                 // keys per tile
 constexpr int kStages = 3;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
+constexpr int kWarpMma = 8, kWarpQ = 9;
 constexpr int kHalfBytes = kTileN * 128;    // one 64-column half of a K or V tile: 16 KB
 constexpr int kStageBytes = 4 * kHalfBytes; // K h0 | K h1 | V h0 | V h1 = 64 KB
 constexpr int kQBufBytes = 2 * 2048;        // two halves of [16 rows x 128 B]
@@ -82,6 +88,7 @@ struct Params {
   const int32_t* plan;
   int bs, hq, hkv;
   int num_slots;
+  int box_rows;  // rows per tiled TMA box (8..64, divides page_size); 0 = gather4 mode
   float scale_log2;
   T* out;
   float* part_o;
@@ -119,7 +126,9 @@ __device__ __forceinline__ Unit get_unit(int unit, int hkv, int bs, int chunk_to
 template <typename T, int G>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map_k,
-                      const __grid_constant__ CUtensorMap map_v) {
+                      const __grid_constant__ CUtensorMap map_v,
+                      const __grid_constant__ CUtensorMap box_k,
+                      const __grid_constant__ CUtensorMap box_v) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -159,8 +168,10 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     fence_barrier_init();
     prefetch_tensormap(&map_k);
     prefetch_tensormap(&map_v);
+    prefetch_tensormap(&box_k);
+    prefetch_tensormap(&box_v);
   }
-  if (warp == 3) tmem_alloc(sbase + Smem::tmem_ptr, kTmemCols);
+  if (warp == kWarpQ) tmem_alloc(sbase + Smem::tmem_ptr, kTmemCols);
   fence_proxy_async_smem();  // zero-fill above must be visible to UMMA operand reads
   tc_fence_before_sync();
   __syncthreads();
@@ -169,44 +180,93 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
   const int32_t* chunk_start = staged ? sChunk : chunk_start_g;
   const int32_t* seq_lens = staged ? sSeq : p.seq_lens;
 
-  if (warp == 0) {
-    // ============================================================ TMA producer (32 lanes)
-    uint32_t tile_count = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
-      const int32_t* slots = p.slot_table + (int64_t)u.r * p.st_stride;
-      const int col0 = u.h * kD;
-      auto load_rows = [&](int t) {
-        int4 rr;
-        const int pos0 = u.kv_begin + t * kTileN + lane * 4;
-        if (pos0 + 3 < u.kv_end_tc) {
-          rr = __ldg(reinterpret_cast<const int4*>(slots + pos0));
+  if (warp < 4) {
+    // ============================================================ TMA producers
+    const int rb = p.box_rows;
+    if (rb > 0 && warp != 0) {
+      // box mode needs a handful of instructions per tile: one warp is plenty
+    } else {
+      uint32_t tile_count = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
+        const int32_t* slots = p.slot_table + (int64_t)u.r * p.st_stride;
+        const int col0 = u.h * kD;
+        // four slots of row group `grp` (rows 4*grp..4*grp+3 of tile t); invalid rows -> out of range
+        auto load_group = [&](int t, int grp) {
+          int4 rr;
+          const int pos0 = u.kv_begin + t * kTileN + grp * 4;
+          if (pos0 + 3 < u.kv_end_tc) {
+            rr = __ldg(reinterpret_cast<const int4*>(slots + pos0));
+          } else {
+            rr.x = pos0 + 0 < u.kv_end_tc ? __ldg(slots + pos0 + 0) : p.num_slots;
+            rr.y = pos0 + 1 < u.kv_end_tc ? __ldg(slots + pos0 + 1) : p.num_slots;
+            rr.z = pos0 + 2 < u.kv_end_tc ? __ldg(slots + pos0 + 2) : p.num_slots;
+            rr.w = pos0 + 3 < u.kv_end_tc ? __ldg(slots + pos0 + 3) : p.num_slots;
+          }
+          return rr;
+        };
+        if (rb == 0) {
+          // ---- gather mode: warp w owns rows 32w..32w+31; lane = (row group, part)
+          const int grp = warp * 8 + (lane >> 2), part = lane & 3;
+          int4 nxt = make_int4(0, 0, 0, 0);
+          if (u.n_tiles > 0) nxt = load_group(0, grp);
+          for (int t = 0; t < u.n_tiles; ++t, ++tile_count) {
+            const int4 cur = nxt;
+            if (t + 1 < u.n_tiles) nxt = load_group(t + 1, grp);
+            const uint32_t stage = tile_count % kStages, phase = (tile_count / kStages) & 1;
+            mbar_wait(bar(kEmpty + stage), phase ^ 1);
+            if (warp == 0 && lane == 0) mbar_arrive_expect_tx(bar(kFull + stage), kStageBytes);
+            __syncwarp();
+            const uint32_t dst = sbase + Smem::stages + stage * kStageBytes + part * kHalfBytes + grp * 512;
+            tma_gather4(dst, (part < 2) ? &map_k : &map_v, bar(kFull + stage), col0 + (part & 1) * 64,
+                        cur.x, cur.y, cur.z, cur.w);
+          }
         } else {
-          rr.x = pos0 + 0 < u.kv_end_tc ? __ldg(slots + pos0 + 0) : p.num_slots;  // out of range row
-          rr.y = pos0 + 1 < u.kv_end_tc ? __ldg(slots + pos0 + 1) : p.num_slots;  //  => zero filled
-          rr.z = pos0 + 2 < u.kv_end_tc ? __ldg(slots + pos0 + 2) : p.num_slots;
-          rr.w = pos0 + 3 < u.kv_end_tc ? __ldg(slots + pos0 + 3) : p.num_slots;
+          // ---- box mode: instruction idx = (box, part); a box is rb consecutive positions of one page
+          const int n_instr = (kTileN / rb) * 4;
+          for (int t = 0; t < u.n_tiles; ++t, ++tile_count) {
+            const uint32_t stage = tile_count % kStages, phase = (tile_count / kStages) & 1;
+            const int tile_begin = u.kv_begin + t * kTileN;
+            // slot of the first row of this lane's boxes (loaded before the wait to overlap latency)
+            int first_slot[2] = {p.num_slots, p.num_slots};
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+              const int idx = lane + it * kWarp;
+              if (idx < n_instr) {
+                const int pb = tile_begin + (idx >> 2) * rb;
+                if (pb < u.kv_end_tc) first_slot[it] = __ldg(slots + pb);
+              }
+            }
+            mbar_wait(bar(kEmpty + stage), phase ^ 1);
+            if (lane == 0) mbar_arrive_expect_tx(bar(kFull + stage), kStageBytes);
+            __syncwarp();
+            const uint32_t sdst = sbase + Smem::stages + stage * kStageBytes;
+            const uint32_t fb = bar(kFull + stage);
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+              const int idx = lane + it * kWarp;
+              if (idx < n_instr) {
+                const int box = idx >> 2, part = idx & 3;
+                const int pb = tile_begin + box * rb;
+                const uint32_t dst = sdst + part * kHalfBytes + box * rb * 128;
+                const int col = col0 + (part & 1) * 64;
+                if (pb + rb <= u.kv_end_tc || pb >= u.kv_end_tc) {
+                  // whole box valid (or wholly past the end: row coordinate out of range => zeros)
+                  tma_load_2d(dst, (part < 2) ? &box_k : &box_v, fb, col, first_slot[it]);
+                } else {
+                  // the box straddling the end of the range: row-exact gather4, invalid rows zero filled
+                  for (int g4 = 0; g4 < rb / 4; ++g4) {
+                    const int4 rr = load_group(t, box * (rb / 4) + g4);
+                    tma_gather4(dst + g4 * 512, (part < 2) ? &map_k : &map_v, fb, col, rr.x, rr.y, rr.z, rr.w);
+                  }
+                }
+              }
+            }
+          }
         }
-        return rr;
-      };
-      int4 nxt = make_int4(0, 0, 0, 0);
-      if (u.n_tiles > 0) nxt = load_rows(0);
-      for (int t = 0; t < u.n_tiles; ++t, ++tile_count) {
-        const int4 cur = nxt;
-        if (t + 1 < u.n_tiles) nxt = load_rows(t + 1);
-        const uint32_t stage = tile_count % kStages, phase = (tile_count / kStages) & 1;
-        mbar_wait(bar(kEmpty + stage), phase ^ 1);
-        if (lane == 0) mbar_arrive_expect_tx(bar(kFull + stage), kStageBytes);
-        __syncwarp();
-        const uint32_t dst = sbase + Smem::stages + stage * kStageBytes + lane * 512;
-        const uint32_t fb = bar(kFull + stage);
-        tma_gather4(dst + 0 * kHalfBytes, &map_k, fb, col0, cur.x, cur.y, cur.z, cur.w);
-        tma_gather4(dst + 1 * kHalfBytes, &map_k, fb, col0 + 64, cur.x, cur.y, cur.z, cur.w);
-        tma_gather4(dst + 2 * kHalfBytes, &map_v, fb, col0, cur.x, cur.y, cur.z, cur.w);
-        tma_gather4(dst + 3 * kHalfBytes, &map_v, fb, col0 + 64, cur.x, cur.y, cur.z, cur.w);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // ============================================================ UMMA issuer (one thread)
     if (lane == 0) {
       constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
@@ -238,32 +298,44 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
         if (u.n_tiles == 1) umma_commit(bar(kQEmpty + qb));
         for (int j = 0; j < u.n_tiles; ++j) {
           const uint32_t tc = tile_count + j;
-          if (j + 1 < u.n_tiles) {
-            issue_qk(tc + 1, qb);
-            if (j + 2 == u.n_tiles) umma_commit(bar(kQEmpty + qb));  // last QK of this unit issued
-          }
-          mbar_wait(bar(kPFull + (tc & 1)), (tc >> 1) & 1);
-          tc_fence_after_sync();
-          const uint32_t stage = tc % kStages;
-          const uint32_t vb = sbase + Smem::stages + stage * kStageBytes + 2 * kHalfBytes;
-          const uint32_t pb = sbase + Smem::pbuf + (tc & 1) * kPBufBytes;
-          const uint32_t d = tmem_base + 2 * kNPad + (tc & 1) * kNPad;
+          bool need_qk = j + 1 < u.n_tiles, need_pv = true;
+          uint32_t spins = 0;
+          while (need_qk || need_pv) {
+            // PV(j) frees a stage for the producers: never let it queue behind the wait for tile j+1
+            if (need_pv && mbar_try_wait(bar(kPFull + (tc & 1)), (tc >> 1) & 1)) {
+              tc_fence_after_sync();
+              const uint32_t stage = tc % kStages;
+              const uint32_t vb = sbase + Smem::stages + stage * kStageBytes + 2 * kHalfBytes;
+              const uint32_t pb = sbase + Smem::pbuf + (tc & 1) * kPBufBytes;
+              const uint32_t d = tmem_base + 2 * kNPad + (tc & 1) * kNPad;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            // A = V^T (MN-major): 16 keys = two 8-key swizzle atoms of 1024 B; dims 64..127 at +16 KB
-            const uint64_t da = make_smem_desc(vb + kk * 2048, kHalfBytes, 1024, kLayoutSW128);
-            // B = P^T (K-major, no swizzle): 8x16-byte core matrices, k-chunks 128 B apart, n-groups 2 KB
-            const uint64_t db = make_smem_desc(pb + kk * 256, 128, 2048, kLayoutNone);
-            umma_f16_ss(d, da, db, idesc_pv, kk > 0);
+              for (int kk = 0; kk < 8; ++kk) {
+                // A = V^T (MN-major): 16 keys = two 8-key swizzle atoms of 1024 B; dims 64..127 at +16 KB
+                const uint64_t da = make_smem_desc(vb + kk * 2048, kHalfBytes, 1024, kLayoutSW128);
+                // B = P^T (K-major, no swizzle): 8x16-byte core matrices, k-chunks 128 B apart, n-groups 2 KB
+                const uint64_t db = make_smem_desc(pb + kk * 256, 128, 2048, kLayoutNone);
+                umma_f16_ss(d, da, db, idesc_pv, kk > 0);
+              }
+              umma_commit(bar(kOFull + (tc & 1)));
+              umma_commit(bar(kEmpty + stage));
+              need_pv = false;
+            }
+            if (need_qk) {
+              const uint32_t tn = tc + 1;
+              if (mbar_try_wait(bar(kFull + tn % kStages), (tn / kStages) & 1)) {
+                issue_qk(tn, qb);
+                if (j + 2 == u.n_tiles) umma_commit(bar(kQEmpty + qb));  // last QK of this unit issued
+                need_qk = false;
+              }
+            }
+            if (++spins > (1u << 22)) __trap();
           }
-          umma_commit(bar(kOFull + (tc & 1)));
-          umma_commit(bar(kEmpty + stage));
         }
         tile_count += u.n_tiles;
         ++unit_count;
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == kWarpQ) {
     // ============================================================ Q loader
     uint32_t unit_count = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
@@ -283,7 +355,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
       if (lane == 0) mbar_arrive(bar(kQFull + qb));
       ++unit_count;
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ============================================================ softmax / accumulate (128 threads)
     const int ct = tid - 128;          // 0..127 = TMEM lane = key within tile = output dim
     const int cw = warp - 4;           // TMEM lane quadrant of this warp
@@ -430,14 +502,15 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
   // ---------------------------------------------------------------- teardown
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 3) {
+  if (warp == kWarpQ) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
 template <typename T, int G>
-static int launch_g(const Params<T>& p, const CUtensorMap& mk, const CUtensorMap& mv, cudaStream_t st) {
+static int launch_g(const Params<T>& p, const CUtensorMap& mk, const CUtensorMap& mv,
+                    const CUtensorMap& bk, const CUtensorMap& bv, cudaStream_t st) {
   const size_t smem = Smem::total + 1024;
   static bool configured = false;
   if (!configured) {
@@ -445,7 +518,7 @@ static int launch_g(const Params<T>& p, const CUtensorMap& mk, const CUtensorMap
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  attn_decode_tc_kernel<T, G><<<num_sms(), kThreads, smem, st>>>(p, mk, mv);
+  attn_decode_tc_kernel<T, G><<<num_sms(), kThreads, smem, st>>>(p, mk, mv, bk, bv);
   B200_POST_LAUNCH();
   attn_combine_kernel<T><<<dim3(p.bs, p.hq), kHeadDim, 0, st>>>(p.part_o, p.part_ml, p.plan, p.hq, p.out);
   B200_POST_LAUNCH();
@@ -459,15 +532,20 @@ static int launch(const Params<T>& p, cudaStream_t st) {
   const uint64_t cols = (uint64_t)p.hkv * kD;
   if (int rc = get_tensor_map_2d(&mk, p.k_cache, p.num_slots, cols, cols * 2, 64, 1, bf16)) return rc;
   if (int rc = get_tensor_map_2d(&mv, p.v_cache, p.num_slots, cols, cols * 2, 64, 1, bf16)) return rc;
+  CUtensorMap bk = mk, bv = mv;
+  if (p.box_rows > 0) {
+    if (int rc = get_tensor_map_2d(&bk, p.k_cache, p.num_slots, cols, cols * 2, 64, p.box_rows, bf16)) return rc;
+    if (int rc = get_tensor_map_2d(&bv, p.v_cache, p.num_slots, cols, cols * 2, 64, p.box_rows, bf16)) return rc;
+  }
   switch (p.hq / p.hkv) {
-    case 1: return launch_g<T, 1>(p, mk, mv, st);
-    case 2: return launch_g<T, 2>(p, mk, mv, st);
-    case 3: return launch_g<T, 3>(p, mk, mv, st);
-    case 4: return launch_g<T, 4>(p, mk, mv, st);
-    case 5: return launch_g<T, 5>(p, mk, mv, st);
-    case 6: return launch_g<T, 6>(p, mk, mv, st);
-    case 7: return launch_g<T, 7>(p, mk, mv, st);
-    case 8: return launch_g<T, 8>(p, mk, mv, st);
+    case 1: return launch_g<T, 1>(p, mk, mv, bk, bv, st);
+    case 2: return launch_g<T, 2>(p, mk, mv, bk, bv, st);
+    case 3: return launch_g<T, 3>(p, mk, mv, bk, bv, st);
+    case 4: return launch_g<T, 4>(p, mk, mv, bk, bv, st);
+    case 5: return launch_g<T, 5>(p, mk, mv, bk, bv, st);
+    case 6: return launch_g<T, 6>(p, mk, mv, bk, bv, st);
+    case 7: return launch_g<T, 7>(p, mk, mv, bk, bv, st);
+    case 8: return launch_g<T, 8>(p, mk, mv, bk, bv, st);
     default:
       set_error("attn_decode: GQA group size %d not supported (1..8)", p.hq / p.hkv);
       return 1;
@@ -480,8 +558,16 @@ static int launch(const Params<T>& p, cudaStream_t st) {
 int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, const void* v,
                      int64_t v_rs, void* k_cache, void* v_cache, const int32_t* out_loc,
                      const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
-                     const int32_t* plan, int bs, int hq, int hkv, int64_t num_slots, float scale_log2,
-                     void* out, float* part_o, float* part_ml, int dtype, cudaStream_t st) {
+                     const int32_t* plan, int bs, int hq, int hkv, int64_t num_slots, int page_size,
+                     float scale_log2, void* out, float* part_o, float* part_ml, int dtype,
+                     cudaStream_t st) {
+  // rows per tiled TMA box: largest power of two <= min(page_size, 64) that divides page_size
+  int box_rows = 0;
+  if (page_size >= 8) {
+    box_rows = 64;
+    while (box_rows > 8 && (page_size % box_rows) != 0) box_rows >>= 1;
+    if (page_size % box_rows != 0) box_rows = 0;
+  }
   B200_CHECK_ARG(num_slots > 0 && num_slots < (1ll << 31), "attn_decode: bad num_slots %lld",
                  (long long)num_slots);
   B200_CHECK_ARG(st_stride % 4 == 0 && ((uintptr_t)slot_table % 16) == 0,
@@ -489,7 +575,7 @@ int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, c
 #define RUN(T_)                                                                                   \
   dtc::Params<T_> p{(const T_*)q, q_rs, (const T_*)k, k_rs, (const T_*)v, v_rs, (T_*)k_cache,     \
                     (T_*)v_cache, out_loc, slot_table, st_stride, seq_lens, plan, bs, hq, hkv,    \
-                    (int)num_slots, scale_log2, (T_*)out, part_o, part_ml};                       \
+                    (int)num_slots, box_rows, scale_log2, (T_*)out, part_o, part_ml};                       \
   return dtc::launch<T_>(p, st)
   if (dtype == B200_DTYPE_BF16) {
     RUN(__nv_bfloat16);

@@ -324,7 +324,7 @@ using namespace b200;
 
 extern "C" int b200_attn_prefill(const void* q, int64_t q_row_stride, const void* k,
                                  int64_t k_row_stride, const void* v, int64_t v_row_stride,
-                                 void* k_cache, void* v_cache, int64_t num_slots,
+                                 void* k_cache, void* v_cache, int64_t num_slots, int page_size,
                                  const int32_t* out_loc, const int32_t* slot_table,
                                  int64_t slot_table_stride,
                                  const int32_t* seq_lens, const int32_t* cu_seqlens_q, int bs,
@@ -333,6 +333,7 @@ extern "C" int b200_attn_prefill(const void* q, int64_t q_row_stride, const void
                                  int dtype, void* stream) {
   (void)workspace;
   (void)num_slots;
+  (void)page_size;
   (void)workspace_bytes;
   B200_CHECK_ARG(head_dim == kD, "attn_prefill: head_dim must be 128 (got %d)", head_dim);
   B200_CHECK_ARG(bs > 0 && hq > 0 && hkv > 0 && hq % hkv == 0,
