@@ -50,7 +50,7 @@ constexpr int kStages = 3;
 constexpr int kThreads = 384;
 constexpr int kWarpMma = 8, kWarpQ = 9;
 constexpr int kHalfBytes = kTileN * 128;    // one 64-column half of a K or V tile: 16 KB
-constexpr int kStageBytes = 4 * kHalfBytes; // K h0 | K h1 | V h0 | V h1 = 64 KB
+constexpr int kStageBytes = 2 * kHalfBytes; // one K (or V) tile: half 0 | half 1 = 32 KB
 constexpr int kQBufBytes = 2 * 2048;        // two halves of [16 rows x 128 B]
 constexpr int kPBufBytes = 16 * kTileN * 2; // P^T [16 x 128] bf16, no-swizzle K-major
 constexpr int kNPad = 16;                   // UMMA N (query heads of the group, padded)
@@ -59,17 +59,18 @@ constexpr int kMaxBsSmem = 512;
 
 struct Smem {
   // offsets from the 1024-aligned base
-  static constexpr int stages = 0;
-  static constexpr int qbuf = kStages * kStageBytes;
+  static constexpr int kring = 0;                          // K tiles, released right after QK
+  static constexpr int vring = kStages * kStageBytes;      // V tiles, released after PV
+  static constexpr int qbuf = 2 * kStages * kStageBytes;
   static constexpr int pbuf = qbuf + 2 * kQBufBytes;
-  static constexpr int bars = pbuf + 2 * kPBufBytes;      // 16 mbarriers
-  static constexpr int tmem_ptr = bars + 16 * 8;
+  static constexpr int bars = pbuf + 2 * kPBufBytes;      // 22 mbarriers
+  static constexpr int tmem_ptr = bars + 24 * 8;
   static constexpr int red = tmem_ptr + 16;               // [2][4][16] floats (tile max), [4][16] (sums)
   static constexpr int chunk = red + (2 * 4 * 16 + 4 * 16 + 4 * 16) * 4;
   static constexpr int seq = chunk + (kMaxBsSmem + 1) * 4;
   static constexpr int total = seq + kMaxBsSmem * 4;
 };
-enum Bar { kFull = 0, kEmpty = 3, kSFull = 6, kPFull = 8, kOFull = 10, kQFull = 12, kQEmpty = 14 };
+enum Bar { kFullK = 0, kEmptyK = 3, kFullV = 6, kEmptyV = 9, kSFull = 12, kPFull = 14, kOFull = 16, kQFull = 18, kQEmpty = 20 };
 
 template <typename T>
 struct Params {
@@ -155,8 +156,10 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     reinterpret_cast<uint4*>(smem + Smem::qbuf)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(bar(kFull + s), 1);
-      mbar_init(bar(kEmpty + s), 1);
+      mbar_init(bar(kFullK + s), 1);
+      mbar_init(bar(kEmptyK + s), 1);
+      mbar_init(bar(kFullV + s), 1);
+      mbar_init(bar(kEmptyV + s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(kSFull + b), 1);
@@ -182,10 +185,18 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
 
   if (warp < 4) {
     // ============================================================ TMA producers
+    // K and V travel in separate rings (a K tile is dead as soon as QK^T has been issued, a V
+    // tile only after PV), so each has its own producers: box mode warp 0 = K, warp 1 = V;
+    // gather mode warps 0,1 = K rows 0-63 / 64-127, warps 2,3 = V.
     const int rb = p.box_rows;
-    if (rb > 0 && warp != 0) {
-      // box mode needs a handful of instructions per tile: one warp is plenty
+    const int kind = rb > 0 ? warp : (warp >> 1);  // 0 = K, 1 = V
+    if (rb > 0 && warp >= 2) {
+      // box mode needs a handful of instructions per tile: two warps are plenty
     } else {
+      const CUtensorMap* gmap = kind == 0 ? &map_k : &map_v;
+      const CUtensorMap* bmap = kind == 0 ? &box_k : &box_v;
+      const int full0 = kind == 0 ? kFullK : kFullV, empty0 = kind == 0 ? kEmptyK : kEmptyV;
+      const uint32_t ring = sbase + (kind == 0 ? Smem::kring : Smem::vring);
       uint32_t tile_count = 0;
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
         const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
@@ -206,59 +217,46 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
           return rr;
         };
         if (rb == 0) {
-          // ---- gather mode: warp w owns rows 32w..32w+31; lane = (row group, part)
-          const int grp = warp * 8 + (lane >> 2), part = lane & 3;
+          // ---- gather mode: this warp owns 64 rows; lane = (row group, half)
+          const int grp = (warp & 1) * 16 + (lane >> 1), half = lane & 1;
           int4 nxt = make_int4(0, 0, 0, 0);
           if (u.n_tiles > 0) nxt = load_group(0, grp);
           for (int t = 0; t < u.n_tiles; ++t, ++tile_count) {
             const int4 cur = nxt;
             if (t + 1 < u.n_tiles) nxt = load_group(t + 1, grp);
             const uint32_t stage = tile_count % kStages, phase = (tile_count / kStages) & 1;
-            mbar_wait(bar(kEmpty + stage), phase ^ 1);
-            if (warp == 0 && lane == 0) mbar_arrive_expect_tx(bar(kFull + stage), kStageBytes);
+            mbar_wait(bar(empty0 + stage), phase ^ 1);
+            if ((warp & 1) == 0 && lane == 0) mbar_arrive_expect_tx(bar(full0 + stage), kStageBytes);
             __syncwarp();
-            const uint32_t dst = sbase + Smem::stages + stage * kStageBytes + part * kHalfBytes + grp * 512;
-            tma_gather4(dst, (part < 2) ? &map_k : &map_v, bar(kFull + stage), col0 + (part & 1) * 64,
-                        cur.x, cur.y, cur.z, cur.w);
+            const uint32_t dst = ring + stage * kStageBytes + half * kHalfBytes + grp * 512;
+            tma_gather4(dst, gmap, bar(full0 + stage), col0 + half * 64, cur.x, cur.y, cur.z, cur.w);
           }
         } else {
-          // ---- box mode: instruction idx = (box, part); a box is rb consecutive positions of one page
-          const int n_instr = (kTileN / rb) * 4;
+          // ---- box mode: instruction idx = (box, half); a box is rb consecutive positions of one page
+          const int n_instr = (kTileN / rb) * 2;  // <= 32
           for (int t = 0; t < u.n_tiles; ++t, ++tile_count) {
             const uint32_t stage = tile_count % kStages, phase = (tile_count / kStages) & 1;
             const int tile_begin = u.kv_begin + t * kTileN;
-            // slot of the first row of this lane's boxes (loaded before the wait to overlap latency)
-            int first_slot[2] = {p.num_slots, p.num_slots};
-#pragma unroll
-            for (int it = 0; it < 2; ++it) {
-              const int idx = lane + it * kWarp;
-              if (idx < n_instr) {
-                const int pb = tile_begin + (idx >> 2) * rb;
-                if (pb < u.kv_end_tc) first_slot[it] = __ldg(slots + pb);
-              }
-            }
-            mbar_wait(bar(kEmpty + stage), phase ^ 1);
-            if (lane == 0) mbar_arrive_expect_tx(bar(kFull + stage), kStageBytes);
+            const int box = lane >> 1, half = lane & 1;
+            const int pb = tile_begin + box * rb;
+            // slot of the box's first row, loaded before the wait so its latency overlaps
+            int first_slot = p.num_slots;
+            if (lane < n_instr && pb < u.kv_end_tc) first_slot = __ldg(slots + pb);
+            mbar_wait(bar(empty0 + stage), phase ^ 1);
+            if (lane == 0) mbar_arrive_expect_tx(bar(full0 + stage), kStageBytes);
             __syncwarp();
-            const uint32_t sdst = sbase + Smem::stages + stage * kStageBytes;
-            const uint32_t fb = bar(kFull + stage);
-#pragma unroll
-            for (int it = 0; it < 2; ++it) {
-              const int idx = lane + it * kWarp;
-              if (idx < n_instr) {
-                const int box = idx >> 2, part = idx & 3;
-                const int pb = tile_begin + box * rb;
-                const uint32_t dst = sdst + part * kHalfBytes + box * rb * 128;
-                const int col = col0 + (part & 1) * 64;
-                if (pb + rb <= u.kv_end_tc || pb >= u.kv_end_tc) {
-                  // whole box valid (or wholly past the end: row coordinate out of range => zeros)
-                  tma_load_2d(dst, (part < 2) ? &box_k : &box_v, fb, col, first_slot[it]);
-                } else {
-                  // the box straddling the end of the range: row-exact gather4, invalid rows zero filled
-                  for (int g4 = 0; g4 < rb / 4; ++g4) {
-                    const int4 rr = load_group(t, box * (rb / 4) + g4);
-                    tma_gather4(dst + g4 * 512, (part < 2) ? &map_k : &map_v, fb, col, rr.x, rr.y, rr.z, rr.w);
-                  }
+            if (lane < n_instr) {
+              const uint32_t dst = ring + stage * kStageBytes + half * kHalfBytes + box * rb * 128;
+              const uint32_t fb = bar(full0 + stage);
+              const int col = col0 + half * 64;
+              if (pb + rb <= u.kv_end_tc || pb >= u.kv_end_tc) {
+                // whole box valid (or wholly past the end: row coordinate out of range => zeros)
+                tma_load_2d(dst, bmap, fb, col, first_slot);
+              } else {
+                // the box straddling the end of the range: row-exact gather4, invalid rows zero filled
+                for (int g4 = 0; g4 < rb / 4; ++g4) {
+                  const int4 rr = load_group(t, box * (rb / 4) + g4);
+                  tma_gather4(dst + g4 * 512, gmap, fb, col, rr.x, rr.y, rr.z, rr.w);
                 }
               }
             }
@@ -274,10 +272,9 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
       constexpr uint32_t idesc_pv = make_idesc_f16(128, kNPad, kBf16, true, false);
       uint32_t tile_count = 0, unit_count = 0;
       auto issue_qk = [&](uint32_t tc, uint32_t qb) {
-        const uint32_t stage = tc % kStages, phase = (tc / kStages) & 1;
-        mbar_wait(bar(kFull + stage), phase);
+        const uint32_t stage = tc % kStages;
         tc_fence_after_sync();
-        const uint32_t kb = sbase + Smem::stages + stage * kStageBytes;
+        const uint32_t kb = sbase + Smem::kring + stage * kStageBytes;
         const uint32_t qa = sbase + Smem::qbuf + qb * kQBufBytes;
         const uint32_t d = tmem_base + (tc & 1) * kNPad;
 #pragma unroll
@@ -287,6 +284,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
           umma_f16_ss(d, da, db, idesc_qk, kk > 0);
         }
         umma_commit(bar(kSFull + (tc & 1)));
+        umma_commit(bar(kEmptyK + stage));  // the K tile is dead once these MMAs have read it
       };
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
         const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
@@ -294,6 +292,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
         const uint32_t qb = unit_count & 1;
         mbar_wait(bar(kQFull + qb), (unit_count >> 1) & 1);
         tc_fence_after_sync();
+        mbar_wait(bar(kFullK + tile_count % kStages), (tile_count / kStages) & 1);
         issue_qk(tile_count, qb);
         if (u.n_tiles == 1) umma_commit(bar(kQEmpty + qb));
         for (int j = 0; j < u.n_tiles; ++j) {
@@ -302,10 +301,11 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
           uint32_t spins = 0;
           while (need_qk || need_pv) {
             // PV(j) frees a stage for the producers: never let it queue behind the wait for tile j+1
-            if (need_pv && mbar_try_wait(bar(kPFull + (tc & 1)), (tc >> 1) & 1)) {
+            if (need_pv && mbar_test_wait(bar(kPFull + (tc & 1)), (tc >> 1) & 1) &&
+                mbar_test_wait(bar(kFullV + tc % kStages), (tc / kStages) & 1)) {
               tc_fence_after_sync();
               const uint32_t stage = tc % kStages;
-              const uint32_t vb = sbase + Smem::stages + stage * kStageBytes + 2 * kHalfBytes;
+              const uint32_t vb = sbase + Smem::vring + stage * kStageBytes;
               const uint32_t pb = sbase + Smem::pbuf + (tc & 1) * kPBufBytes;
               const uint32_t d = tmem_base + 2 * kNPad + (tc & 1) * kNPad;
 #pragma unroll
@@ -317,18 +317,18 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
                 umma_f16_ss(d, da, db, idesc_pv, kk > 0);
               }
               umma_commit(bar(kOFull + (tc & 1)));
-              umma_commit(bar(kEmpty + stage));
+              umma_commit(bar(kEmptyV + stage));
               need_pv = false;
             }
             if (need_qk) {
               const uint32_t tn = tc + 1;
-              if (mbar_try_wait(bar(kFull + tn % kStages), (tn / kStages) & 1)) {
+              if (mbar_test_wait(bar(kFullK + tn % kStages), (tn / kStages) & 1)) {
                 issue_qk(tn, qb);
                 if (j + 2 == u.n_tiles) umma_commit(bar(kQEmpty + qb));  // last QK of this unit issued
                 need_qk = false;
               }
             }
-            if (++spins > (1u << 22)) __trap();
+            if (++spins > (1u << 28)) __trap();
           }
         }
         tile_count += u.n_tiles;
@@ -366,13 +366,24 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     uint32_t tile_count = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
       const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
-      float acc[G], l_thr[G], m_run[G], alpha_prev[G];
+      float acc[G], l_thr[G], m_run[G], alpha_prev[G], q_new[G];
+      float kn = 0.f, vn = 0.f;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         acc[g] = 0.f;
         l_thr[g] = 0.f;
         m_run[g] = -INFINITY;
         alpha_prev[g] = 0.f;
+        q_new[g] = 0.f;
+      }
+      if (u.last_chunk) {
+        // operands of the appended token's score / value: issue the loads now, use them in the
+        // epilogue -- their latency hides behind the tile loop
+        const T* qrow = p.q + (int64_t)u.r * p.q_rs + (int64_t)(u.h * G) * kD + ct;
+#pragma unroll
+        for (int g = 0; g < G; ++g) q_new[g] = DTypeTraits<T>::to_float(qrow[g * kD]);
+        kn = DTypeTraits<T>::to_float(p.k_new[(int64_t)u.r * p.k_rs + u.h * kD + ct]);
+        vn = DTypeTraits<T>::to_float(p.v_new[(int64_t)u.r * p.v_rs + u.h * kD + ct]);
       }
       auto accumulate_o = [&](uint32_t tc) {
         mbar_wait(bar(kOFull + (tc & 1)), (tc >> 1) & 1);
@@ -426,15 +437,11 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
       // ---- per-unit reductions on CUDA cores: row sums, and the appended token
       float pnew[G];
       {
-        const T* qrow = p.q + (int64_t)u.r * p.q_rs + (int64_t)(u.h * G) * kD + ct;
-        const float kn = u.last_chunk
-                             ? DTypeTraits<T>::to_float(p.k_new[(int64_t)u.r * p.k_rs + u.h * kD + ct])
-                             : 0.f;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const float ls = warp_sum(l_thr[g]);
           float sn = 0.f;
-          if (u.last_chunk) sn = warp_sum(DTypeTraits<T>::to_float(qrow[g * kD]) * kn);
+          if (u.last_chunk) sn = warp_sum(q_new[g] * kn);
           if (lane == 0) {
             red_sum[cw * 16 + g] = ls;
             red_new[cw * 16 + g] = sn;
@@ -449,7 +456,6 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
         pnew[g] = 0.f;
       }
       if (u.last_chunk) {
-        const float vn = DTypeTraits<T>::to_float(p.v_new[(int64_t)u.r * p.v_rs + u.h * kD + ct]);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const float s_new = (red_new[g] + red_new[16 + g] + red_new[32 + g] + red_new[48 + g]) * p.scale_log2;
