@@ -54,8 +54,9 @@ constexpr int kStageBytes = 2 * kHalfBytes; // one K (or V) tile: half 0 | half 
 constexpr int kQBufBytes = 2 * 2048;        // two halves of [16 rows x 128 B]
 constexpr int kPBufBytes = 16 * kTileN * 2; // P^T [16 x 128] bf16, no-swizzle K-major
 constexpr int kNPad = 16;                   // UMMA N (query heads of the group, padded)
-constexpr int kTmemCols = 64;               // S^T: 0,16  O^T: 32,48
-constexpr int kMaxBsSmem = 512;
+constexpr int kNumS = 4;                    // max S^T buffers in TMEM (QK^T look-ahead), runtime p.num_s
+constexpr int kTmemCols = 128;              // S^T: kNumS x 16 columns, O^T: 2 x 16 columns
+constexpr int kMaxUnitsSmem = 96;          // per-CTA work units decoded once into smem
 
 struct Smem {
   // offsets from the 1024-aligned base
@@ -66,11 +67,10 @@ struct Smem {
   static constexpr int bars = pbuf + 2 * kPBufBytes;      // 22 mbarriers
   static constexpr int tmem_ptr = bars + 24 * 8;
   static constexpr int red = tmem_ptr + 16;               // [2][4][16] floats (tile max), [4][16] (sums)
-  static constexpr int chunk = red + (2 * 4 * 16 + 4 * 16 + 4 * 16) * 4;
-  static constexpr int seq = chunk + (kMaxBsSmem + 1) * 4;
-  static constexpr int total = seq + kMaxBsSmem * 4;
+  static constexpr int units = red + (2 * 4 * 16 + 4 * 16 + 4 * 16) * 4;  // decoded work units
+  static constexpr int total = units + kMaxUnitsSmem * 40;
 };
-enum Bar { kFullK = 0, kEmptyK = 3, kFullV = 6, kEmptyV = 9, kSFull = 12, kPFull = 14, kOFull = 16, kQFull = 18, kQEmpty = 20 };
+enum Bar { kFullK = 0, kEmptyK = 3, kFullV = 6, kEmptyV = 9, kSFull = 12, kPFull = 16, kOFull = 18, kQFull = 20, kQEmpty = 22 };
 
 template <typename T>
 struct Params {
@@ -90,6 +90,7 @@ struct Params {
   int bs, hq, hkv;
   int num_slots;
   int box_rows;  // rows per tiled TMA box (8..64, divides page_size); 0 = gather4 mode
+  int num_s;     // S^T buffers in use (2..kNumS)
   float scale_log2;
   T* out;
   float* part_o;
@@ -98,8 +99,9 @@ struct Params {
 
 struct Unit {
   int r, c, h, n_chunks, kv_len, kv_begin, kv_end_tc, n_tiles;
-  bool last_chunk;
+  int last_chunk;
 };
+static_assert(sizeof(Unit) <= 40, "Unit must fit its smem slot");
 
 __device__ __forceinline__ Unit get_unit(int unit, int hkv, int bs, int chunk_tokens,
                                          const int32_t* chunk_start, const int32_t* seq_lens) {
@@ -138,19 +140,26 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
   auto bar = [&](int i) { return sbase + Smem::bars + i * 8; };
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
   float* red = reinterpret_cast<float*>(smem + Smem::red);
-  int32_t* sChunk = reinterpret_cast<int32_t*>(smem + Smem::chunk);
-  int32_t* sSeq = reinterpret_cast<int32_t*>(smem + Smem::seq);
+  uint8_t* sUnits = smem + Smem::units;
 
   const int chunk_tokens = p.plan[0];
   const int total_units = p.plan[1] * p.hkv;
-  const int32_t* chunk_start_g = p.plan + kPlanHeader;
-  const bool staged = p.bs <= kMaxBsSmem;
+  const int32_t* chunk_start = p.plan + kPlanHeader;
+  const int32_t* seq_lens = p.seq_lens;
 
   // ---------------------------------------------------------------- one-time setup
-  if (staged) {
-    for (int i = tid; i <= p.bs; i += kThreads) sChunk[i] = chunk_start_g[i];
-    for (int i = tid; i < p.bs; i += kThreads) sSeq[i] = p.seq_lens[i];
+  // every role walks the same unit list: decode it once (one binary search per thread, in
+  // parallel) instead of once per role per unit
+  for (int i = tid; i < kMaxUnitsSmem; i += kThreads) {
+    const int unit = blockIdx.x + i * gridDim.x;
+    if (unit < total_units)
+      *reinterpret_cast<Unit*>(sUnits + i * 40) = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
   }
+  auto unit_at = [&](int unit) {
+    const int i = (unit - (int)blockIdx.x) / (int)gridDim.x;
+    if (i < kMaxUnitsSmem) return *reinterpret_cast<const Unit*>(sUnits + i * 40);
+    return get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
+  };
   // zero the operand buffers whose padding rows (heads >= G) are never written again
   for (int i = tid; i < (2 * kQBufBytes + 2 * kPBufBytes) / 16; i += kThreads)
     reinterpret_cast<uint4*>(smem + Smem::qbuf)[i] = make_uint4(0, 0, 0, 0);
@@ -161,8 +170,8 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
       mbar_init(bar(kFullV + s), 1);
       mbar_init(bar(kEmptyV + s), 1);
     }
+    for (int b = 0; b < kNumS; ++b) mbar_init(bar(kSFull + b), 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar(kSFull + b), 1);
       mbar_init(bar(kPFull + b), 128);
       mbar_init(bar(kOFull + b), 1);
       mbar_init(bar(kQFull + b), 1);
@@ -180,8 +189,6 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_s;
-  const int32_t* chunk_start = staged ? sChunk : chunk_start_g;
-  const int32_t* seq_lens = staged ? sSeq : p.seq_lens;
 
   if (warp < 4) {
     // ============================================================ TMA producers
@@ -199,7 +206,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
       const uint32_t ring = sbase + (kind == 0 ? Smem::kring : Smem::vring);
       uint32_t tile_count = 0;
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
+        const Unit u = unit_at(unit);
         const int32_t* slots = p.slot_table + (int64_t)u.r * p.st_stride;
         const int col0 = u.h * kD;
         // four slots of row group `grp` (rows 4*grp..4*grp+3 of tile t); invalid rows -> out of range
@@ -249,16 +256,10 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
               const uint32_t dst = ring + stage * kStageBytes + half * kHalfBytes + box * rb * 128;
               const uint32_t fb = bar(full0 + stage);
               const int col = col0 + half * 64;
-              if (pb + rb <= u.kv_end_tc || pb >= u.kv_end_tc) {
-                // whole box valid (or wholly past the end: row coordinate out of range => zeros)
-                tma_load_2d(dst, bmap, fb, col, first_slot);
-              } else {
-                // the box straddling the end of the range: row-exact gather4, invalid rows zero filled
-                for (int g4 = 0; g4 < rb / 4; ++g4) {
-                  const int4 rr = load_group(t, box * (rb / 4) + g4);
-                  tma_gather4(dst + g4 * 512, gmap, fb, col, rr.x, rr.y, rr.z, rr.w);
-                }
-              }
+              // A box reaching past the end of the range still lies inside the request's page; the
+              // extra K rows are masked by position and the extra V rows are zeroed in smem by the
+              // softmax warps before PV.  A box wholly past the end gets an out-of-range row => zeros.
+              tma_load_2d(dst, bmap, fb, col, first_slot);
             }
           }
         }
@@ -270,76 +271,93 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
       constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
       constexpr uint32_t idesc_qk = make_idesc_f16(128, kNPad, kBf16, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, kNPad, kBf16, true, false);
-      uint32_t tile_count = 0, unit_count = 0;
-      auto issue_qk = [&](uint32_t tc, uint32_t qb) {
-        const uint32_t stage = tc % kStages;
-        tc_fence_after_sync();
-        const uint32_t kb = sbase + Smem::kring + stage * kStageBytes;
-        const uint32_t qa = sbase + Smem::qbuf + qb * kQBufBytes;
-        const uint32_t d = tmem_base + (tc & 1) * kNPad;
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t da = make_smem_desc(kb + (kk >> 2) * kHalfBytes + (kk & 3) * 32, 16, 1024, kLayoutSW128);
-          const uint64_t db = make_smem_desc(qa + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024, kLayoutSW128);
-          umma_f16_ss(d, da, db, idesc_qk, kk > 0);
-        }
-        umma_commit(bar(kSFull + (tc & 1)));
-        umma_commit(bar(kEmptyK + stage));  // the K tile is dead once these MMAs have read it
+      // Two cursors walk the same unit/tile sequence: QK^T may run up to kNumS tiles (also across
+      // unit boundaries) ahead of PV, so K tiles are consumed -- and their ring slots recycled -- as
+      // soon as they land, independent of the softmax latency.
+      struct Cursor {
+        int unit;        // current unit id (grid-strided)
+        int j;           // tile within the unit
+        int n_tiles;     // tiles of the current unit
+        uint32_t tc;     // global tile counter
+        uint32_t uc;     // global counter of units with tiles
       };
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
-        if (u.n_tiles == 0) continue;
-        const uint32_t qb = unit_count & 1;
-        mbar_wait(bar(kQFull + qb), (unit_count >> 1) & 1);
-        tc_fence_after_sync();
-        mbar_wait(bar(kFullK + tile_count % kStages), (tile_count / kStages) & 1);
-        issue_qk(tile_count, qb);
-        if (u.n_tiles == 1) umma_commit(bar(kQEmpty + qb));
-        for (int j = 0; j < u.n_tiles; ++j) {
-          const uint32_t tc = tile_count + j;
-          bool need_qk = j + 1 < u.n_tiles, need_pv = true;
-          uint32_t spins = 0;
-          while (need_qk || need_pv) {
-            // PV(j) frees a stage for the producers: never let it queue behind the wait for tile j+1
-            if (need_pv && mbar_test_wait(bar(kPFull + (tc & 1)), (tc >> 1) & 1) &&
-                mbar_test_wait(bar(kFullV + tc % kStages), (tc / kStages) & 1)) {
-              tc_fence_after_sync();
-              const uint32_t stage = tc % kStages;
-              const uint32_t vb = sbase + Smem::vring + stage * kStageBytes;
-              const uint32_t pb = sbase + Smem::pbuf + (tc & 1) * kPBufBytes;
-              const uint32_t d = tmem_base + 2 * kNPad + (tc & 1) * kNPad;
+      auto seek = [&](Cursor& c) {  // position on the next unit that has tiles
+        while (c.unit < total_units) {
+          c.n_tiles = unit_at(c.unit).n_tiles;
+          if (c.n_tiles > 0) return;
+          c.unit += gridDim.x;
+        }
+        c.n_tiles = 0;
+      };
+      auto advance = [&](Cursor& c) {
+        ++c.tc;
+        if (++c.j == c.n_tiles) {
+          c.j = 0;
+          ++c.uc;
+          c.unit += gridDim.x;
+          seek(c);
+        }
+      };
+      Cursor qk{(int)blockIdx.x, 0, 0, 0, 0}, pv{(int)blockIdx.x, 0, 0, 0, 0};
+      seek(qk);
+      seek(pv);
+      uint32_t spins = 0;
+      while (pv.unit < total_units) {
+        bool progress = false;
+        // ---- S^T[tile] = K_tile . Q^T
+        if (qk.unit < total_units && qk.tc - pv.tc < (uint32_t)p.num_s) {
+          const uint32_t tc = qk.tc, stage = tc % kStages, qb = qk.uc & 1;
+          if (mbar_test_wait(bar(kFullK + stage), (tc / kStages) & 1) &&
+              (qk.j > 0 || mbar_test_wait(bar(kQFull + qb), (qk.uc >> 1) & 1))) {
+            tc_fence_after_sync();
+            const uint32_t kb = sbase + Smem::kring + stage * kStageBytes;
+            const uint32_t qa = sbase + Smem::qbuf + qb * kQBufBytes;
+            const uint32_t d = tmem_base + (tc % p.num_s) * kNPad;
 #pragma unroll
-              for (int kk = 0; kk < 8; ++kk) {
-                // A = V^T (MN-major): 16 keys = two 8-key swizzle atoms of 1024 B; dims 64..127 at +16 KB
-                const uint64_t da = make_smem_desc(vb + kk * 2048, kHalfBytes, 1024, kLayoutSW128);
-                // B = P^T (K-major, no swizzle): 8x16-byte core matrices, k-chunks 128 B apart, n-groups 2 KB
-                const uint64_t db = make_smem_desc(pb + kk * 256, 128, 2048, kLayoutNone);
-                umma_f16_ss(d, da, db, idesc_pv, kk > 0);
-              }
-              umma_commit(bar(kOFull + (tc & 1)));
-              umma_commit(bar(kEmptyV + stage));
-              need_pv = false;
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t da = make_smem_desc(kb + (kk >> 2) * kHalfBytes + (kk & 3) * 32, 16, 1024, kLayoutSW128);
+              const uint64_t db = make_smem_desc(qa + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024, kLayoutSW128);
+              umma_f16_ss(d, da, db, idesc_qk, kk > 0);
             }
-            if (need_qk) {
-              const uint32_t tn = tc + 1;
-              if (mbar_test_wait(bar(kFullK + tn % kStages), (tn / kStages) & 1)) {
-                issue_qk(tn, qb);
-                if (j + 2 == u.n_tiles) umma_commit(bar(kQEmpty + qb));  // last QK of this unit issued
-                need_qk = false;
-              }
-            }
-            if (++spins > (1u << 28)) __trap();
+            umma_commit(bar(kSFull + tc % p.num_s));
+            umma_commit(bar(kEmptyK + stage));  // the K tile is dead once these MMAs have read it
+            if (qk.j + 1 == qk.n_tiles) umma_commit(bar(kQEmpty + qb));  // last QK of the unit
+            advance(qk);
+            progress = true;
           }
         }
-        tile_count += u.n_tiles;
-        ++unit_count;
+        // ---- O^T[tile] = V_tile^T . P^T
+        if (pv.tc < qk.tc) {
+          const uint32_t tc = pv.tc, stage = tc % kStages;
+          if (mbar_test_wait(bar(kPFull + (tc & 1)), (tc >> 1) & 1) &&
+              mbar_test_wait(bar(kFullV + stage), (tc / kStages) & 1)) {
+            tc_fence_after_sync();
+            const uint32_t vb = sbase + Smem::vring + stage * kStageBytes;
+            const uint32_t pb = sbase + Smem::pbuf + (tc & 1) * kPBufBytes;
+            const uint32_t d = tmem_base + kNumS * kNPad + (tc & 1) * kNPad;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              // A = V^T (MN-major): 16 keys = two 8-key swizzle atoms of 1024 B; dims 64..127 at +16 KB
+              const uint64_t da = make_smem_desc(vb + kk * 2048, kHalfBytes, 1024, kLayoutSW128);
+              // B = P^T (K-major, no swizzle): 8x16-byte core matrices, k-chunks 128 B apart, n-groups 2 KB
+              const uint64_t db = make_smem_desc(pb + kk * 256, 128, 2048, kLayoutNone);
+              umma_f16_ss(d, da, db, idesc_pv, kk > 0);
+            }
+            umma_commit(bar(kOFull + (tc & 1)));
+            umma_commit(bar(kEmptyV + stage));
+            advance(pv);
+            progress = true;
+          }
+        }
+        if (progress) spins = 0;
+        else if (++spins > (1u << 28)) __trap();
       }
     }
   } else if (warp == kWarpQ) {
     // ============================================================ Q loader
     uint32_t unit_count = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
+      const Unit u = unit_at(unit);
       if (u.n_tiles == 0) continue;
       const uint32_t qb = unit_count & 1;
       mbar_wait(bar(kQEmpty + qb), ((unit_count >> 1) & 1) ^ 1);
@@ -365,7 +383,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     float* red_new = red_sum + 4 * 16; // [4][16]
     uint32_t tile_count = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      const Unit u = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
+      const Unit u = unit_at(unit);
       float acc[G], l_thr[G], m_run[G], alpha_prev[G], q_new[G];
       float kn = 0.f, vn = 0.f;
 #pragma unroll
@@ -389,19 +407,31 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
         mbar_wait(bar(kOFull + (tc & 1)), (tc >> 1) & 1);
         tc_fence_after_sync();
         uint32_t o[16];
-        tmem_ld_x16(tmem_base + lane_base + 2 * kNPad + (tc & 1) * kNPad, o);
+        tmem_ld_x16(tmem_base + lane_base + kNumS * kNPad + (tc & 1) * kNPad, o);
         tmem_wait_ld();
 #pragma unroll
         for (int g = 0; g < G; ++g) acc[g] = acc[g] * alpha_prev[g] + __uint_as_float(o[g]);
       };
       for (int j = 0; j < u.n_tiles; ++j) {
         const uint32_t tc = tile_count + j;
-        mbar_wait(bar(kSFull + (tc & 1)), (tc >> 1) & 1);
+        mbar_wait(bar(kSFull + tc % p.num_s), (tc / p.num_s) & 1);
         tc_fence_after_sync();
         uint32_t s[16];
-        tmem_ld_x16(tmem_base + lane_base + (tc & 1) * kNPad, s);
+        tmem_ld_x16(tmem_base + lane_base + (tc % p.num_s) * kNPad, s);
         tmem_wait_ld();
-        const bool valid = u.kv_begin + j * kTileN + ct < u.kv_end_tc;
+        const int n_valid = u.kv_end_tc - (u.kv_begin + j * kTileN);  // >= 1
+        const bool valid = ct < n_valid;
+        if (p.box_rows > 0 && n_valid < kTileN) {
+          // box mode, last tile of the range: the V rows past the end hold whatever the page holds
+          // (possibly NaN bit patterns): zero them so that 0 * garbage cannot reach the output
+          const uint32_t stage = tc % kStages;
+          mbar_wait(bar(kFullV + stage), (tc / kStages) & 1);
+          uint8_t* vt = smem + Smem::vring + stage * kStageBytes;
+          for (int idx = ct; idx < (kTileN - n_valid) * 16; idx += 128) {
+            const int row = n_valid + (idx >> 4), c16 = idx & 15;
+            *reinterpret_cast<uint4*>(vt + (c16 >> 3) * kHalfBytes + row * 128 + (c16 & 7) * 16) = make_uint4(0, 0, 0, 0);
+          }
+        }
         float sv[G];
         float* rm = red_max + (tc & 1) * 64;
 #pragma unroll
@@ -560,6 +590,8 @@ static int launch(const Params<T>& p, cudaStream_t st) {
 
 }  // namespace dtc
 
+extern std::atomic<int> g_decode_lookahead;
+
 // entry used by b200_attn_decode (attn_decode.cu)
 int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, const void* v,
                      int64_t v_rs, void* k_cache, void* v_cache, const int32_t* out_loc,
@@ -567,6 +599,9 @@ int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, c
                      const int32_t* plan, int bs, int hq, int hkv, int64_t num_slots, int page_size,
                      float scale_log2, void* out, float* part_o, float* part_ml, int dtype,
                      cudaStream_t st) {
+  int num_s = g_decode_lookahead.load();
+  if (num_s < 2) num_s = 2;
+  if (num_s > dtc::kNumS) num_s = dtc::kNumS;
   // rows per tiled TMA box: largest power of two <= min(page_size, 64) that divides page_size
   int box_rows = 0;
   if (page_size >= 8) {
@@ -581,7 +616,7 @@ int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, c
 #define RUN(T_)                                                                                   \
   dtc::Params<T_> p{(const T_*)q, q_rs, (const T_*)k, k_rs, (const T_*)v, v_rs, (T_*)k_cache,     \
                     (T_*)v_cache, out_loc, slot_table, st_stride, seq_lens, plan, bs, hq, hkv,    \
-                    (int)num_slots, box_rows, scale_log2, (T_*)out, part_o, part_ml};                       \
+                    (int)num_slots, box_rows, num_s, scale_log2, (T_*)out, part_o, part_ml};                       \
   return dtc::launch<T_>(p, st)
   if (dtype == B200_DTYPE_BF16) {
     RUN(__nv_bfloat16);

@@ -47,7 +47,14 @@ def _run_case(b200, *, page_size, hq, hkv, lens, phase, seed=0, share_prefix=Non
     w = make_world(seed=seed, page_size=page_size, hq=hq, hkv=hkv, layers=layers,
                    max_reqs=max(len(lens), pad_to or 0) + 1, max_seq=max_seq, dtype=dtype)
     add_requests(w, lens, share_prefix_from=share_prefix)
+    # every pool row no request owns is poisoned with NaN: unused page tails / free pages hold
+    # arbitrary bits in a real engine (torch.empty pool) and must never leak into a result
+    used = np.zeros(w.pool_cpu.shape[2], dtype=bool)
+    for (t, _, d) in w.reqs:
+        used[w.page_table[t, :d]] = True
     gw = GpuWorld(b200, w)
+    gw.pool._kv_buffer.view(2, w.layers, -1, hkv, w.d)[:, :, torch.from_numpy(~used).cuda()] = float("nan")
+    pool_before = gw.pool._kv_buffer.view(2, w.layers, -1, hkv, w.d)[0, layer].clone()
     batch = gw.batch(phase, pad_to=pad_to)
     triples = list(w.reqs)
     if pad_to:
@@ -80,7 +87,7 @@ def _run_case(b200, *, page_size, hq, hkv, lens, phase, seed=0, share_prefix=Non
     # nothing else in the pool moved
     mask = torch.ones(kc.shape[0], dtype=torch.bool)
     mask[torch.from_numpy(ref_md.out_loc.astype(np.int64))] = False
-    assert torch.equal(kc[mask].view(torch.int16), w.pool_cpu[0, layer][mask].view(torch.int16))
+    assert torch.equal(kc[mask].view(torch.int16), pool_before.cpu()[mask].view(torch.int16))
     return rel
 
 

@@ -27,11 +27,15 @@ def main():
     ap.add_argument("--page-size", type=int, default=64)
     ap.add_argument("--hq", type=int, default=bench.HQ)
     ap.add_argument("--hkv", type=int, default=bench.HKV)
+    ap.add_argument("--opt", action="append", default=[], help="name=value for b200_set_option")
     args = ap.parse_args()
     bench.L = args.layers
     bench.HQ, bench.HKV = args.hq, args.hkv
     pkg = importlib.import_module("mini-sglang_b200")
     pkg.build_native()
+    for o in args.opt:
+        k, v = o.split("=")
+        pkg._cabi.set_option(k, int(v))
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     sched = bench.Schedule()
@@ -48,6 +52,7 @@ def main():
             r.backend.prepare_metadata(batch)
             qs = [r.qkv[l, :bs].split([hq * D, hkv * D, hkv * D], dim=-1) for l in range(args.layers)]
             nbytes = bench.decode_bytes_per_layer([(x.table_idx, x.cached_len, x.device_len) for x in batch.padded_reqs], hq, hkv)
+            times = []
             for rep in range(args.reps):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -60,9 +65,13 @@ def main():
                 e1.record()
                 e1.synchronize()
                 us = e0.elapsed_time(e1) * 1e3 / args.layers
+                times.append(us)
+                if rep < args.reps - 1:
+                    continue
+                us = sorted(times)[len(times) // 2]
                 if args.what == "decode":
                     print(f"decode bs={bs} sum_kv={sum(x[2] for x in tr)} : {us:.1f} us/layer, {nbytes / us / 1e3:.0f} GB/s "
-                          f"({nbytes / us / 1e3 / peaks['hbm_gbs']:.3f} of {peaks['source']} HBM peak) plan={batch.attn_metadata.decode_plan[:3].tolist()}")
+                          f"({nbytes / us / 1e3 / peaks['hbm_gbs']:.3f} of {peaks['source']} HBM peak; min {min(times):.1f} us) opts={args.opt} plan={batch.attn_metadata.decode_plan[:3].tolist()}")
                 else:
                     eb = bs * (hq + hkv) * D * 2 * 2
                     print(f"qknorm_rope bs={bs}: {us:.1f} us/layer, {eb / us / 1e3:.0f} GB/s")
