@@ -42,7 +42,9 @@ B200_API uint64_t b200_launch_count(void);
 /* 1 if the library was compiled for sm_100a and the current device is CC 10.x. */
 B200_API int b200_device_supported(void);
 /* Kernel selection knobs (debug / cross-checking only; defaults are the product path):
- *   "decode_impl": 1 = tcgen05 + TMA-gather4 kernel (default), 0 = cp.async / CUDA-core kernel.
+ *   "decode_impl": 1 = tcgen05 + TMA kernel (default), 0 = cp.async / CUDA-core kernel.
+ *   "decode_lookahead": S^T buffers the UMMA issuer may run ahead (2..4, default 4).
+ *   "decode_fused_combine": 1 = merge split-KV partials inside the decode launch, 0 = combine kernel (default).
  * Returns the previous value, or -1 for an unknown name. */
 B200_API int b200_set_option(const char* name, int value);
 
@@ -103,12 +105,15 @@ B200_API int b200_qknorm_rope_inplace(void* q, void* k, const void* q_weight, co
  *       cu_seqlens_q[bs+1]      = exclusive cumsum(device_len - cached_len)
  *       cu_seqlens_k[bs+1]      = exclusive cumsum(device_len)
  *       slot_table[bs][slot_table_stride] : row r = page_table[table_idx_r][0:width]
- *       decode_plan[4 + bs + 1] : {chunk_tokens, total_chunks, bs, 0, chunk_start[bs+1]}
+ *       decode_plan[b200_decode_plan_ints(bs)] :
+ *         {chunk_tokens, total_chunks, bs, 0, chunk_start[bs+1], order[total_chunks]}
  *         (split-KV work list for b200_attn_decode: request r owns chunks
- *          [chunk_start[r], chunk_start[r+1]) of chunk_tokens tokens each).
+ *          [chunk_start[r], chunk_start[r+1]) of chunk_tokens tokens each; order[] lists the
+ *          (request, chunk) items largest first, entry = r | chunk << 16 | n_chunks << 20).
  *     width = number of table columns to copy (>= max device_len, <= both strides).
  *     num_ctas_hint = persistent grid size the decode kernel will use (0 = default).
  * ------------------------------------------------------------------------------------- */
+B200_API size_t b200_decode_plan_ints(int bs); /* = 4 + (bs + 1) + 16 * bs */
 B200_API int b200_build_metadata(const int32_t* req_info, int bs, const int32_t* page_table,
                         int64_t page_table_stride, int32_t* seq_lens, int32_t* cu_seqlens_q,
                         int32_t* cu_seqlens_k, int32_t* slot_table, int64_t slot_table_stride,
@@ -131,7 +136,8 @@ B200_API int b200_build_metadata(const int32_t* req_info, int bs, const int32_t*
  *       INCLUDING the tokens appended by this call.
  *     out [nnz, hq, head_dim] contiguous.  head_dim must be 128.
  *     workspace: b200_attn_workspace_bytes(max_bs, hq) bytes, owned by the caller, may be
- *       shared across layers (stream ordered).
+ *       shared across layers (stream ordered).  It must be ZERO-FILLED once before its first use
+ *       (it holds the split-KV arrival counters, which every launch leaves at zero again).
  * ------------------------------------------------------------------------------------- */
 B200_API size_t b200_attn_workspace_bytes(int max_bs, int hq, int head_dim);
 

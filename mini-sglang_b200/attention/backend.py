@@ -54,6 +54,15 @@ def host_req_info(reqs: Sequence) -> Tuple[List[int], int, int]:
     return flat, max_q, max_k
 
 
+_MAX_SPLITS = 16
+
+
+def plan_ints(bs: int) -> int:
+    """Size of the split-KV decode plan (``b200_decode_plan_ints``): header, chunk_start[bs+1],
+    size-sorted work order (at most 16 chunks per request)."""
+    return _PLAN_HEADER + bs + 1 + _MAX_SPLITS * bs
+
+
 def small_block_layout(bs: int) -> Tuple[int, int, int, int, int]:
     """Offsets (in int32) of seq_lens | cu_q | cu_k | plan inside the per-batch small block; each
     section 16-byte aligned.  Returns (off_seq, off_cuq, off_cuk, off_plan, total)."""
@@ -61,7 +70,7 @@ def small_block_layout(bs: int) -> Tuple[int, int, int, int, int]:
     off_cuq = _align(bs, 4)
     off_cuk = off_cuq + _align(bs + 1, 4)
     off_plan = off_cuk + _align(bs + 1, 4)
-    total = off_plan + _align(_PLAN_HEADER + bs + 1, 4)
+    total = off_plan + _align(plan_ints(bs), 4)
     return off_seq, off_cuq, off_cuk, off_plan, total
 
 
@@ -75,7 +84,7 @@ class B200Metadata(BaseAttnMetadata):
     max_seqlen_k: int
     max_seqlen_q: int
     page_table: torch.Tensor  # int32 [bs, >= max_seqlen_k] token-granular slot snapshot
-    decode_plan: torch.Tensor  # int32 [4 + bs + 1] split-KV plan (see include/b200attn.h)
+    decode_plan: torch.Tensor  # int32 [4 + bs + 1 + 16 bs] split-KV plan (see include/b200attn.h)
     small_block: torch.Tensor  # the contiguous buffer the four small tensors are views of
     bs: int
 
@@ -134,7 +143,8 @@ class B200AttnBackend(BaseAttnBackend):
                 raise RuntimeError("attention workspace must be sized before graph capture")
             want = max(bs, self.max_graph_bs, 256)
             nbytes = self._lib.b200_attn_workspace_bytes(want, self.qo_head_local, self.head_dim)
-            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            # zero-filled once: holds the split-KV arrival counters (left at zero by every launch)
+            self._workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
             self._workspace_bs = want
         return self._workspace
 
@@ -157,7 +167,7 @@ class B200AttnBackend(BaseAttnBackend):
         seq_lens = small[off_seq : off_seq + bs]
         cu_q = small[off_cuq : off_cuq + bs + 1]
         cu_k = small[off_cuk : off_cuk + bs + 1]
-        plan = small[off_plan : off_plan + _PLAN_HEADER + bs + 1]
+        plan = small[off_plan : off_plan + plan_ints(bs)]
         _cabi.check(
             self._lib.b200_build_metadata(
                 info.data_ptr(), bs, page_table.data_ptr(), page_table.stride(0),
@@ -268,7 +278,7 @@ class B200AttnBackend(BaseAttnBackend):
             max_seqlen_k=max_k,
             max_seqlen_q=1,
             page_table=self.capture.page_table[:bs, :],
-            decode_plan=blk[off_plan : off_plan + _PLAN_HEADER + bs + 1],
+            decode_plan=blk[off_plan : off_plan + plan_ints(bs)],
             small_block=blk,
             bs=bs,
         )

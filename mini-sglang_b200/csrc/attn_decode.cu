@@ -337,7 +337,8 @@ using namespace b200;
 
 extern "C" size_t b200_attn_workspace_bytes(int max_bs, int hq, int head_dim) {
   const size_t items = (size_t)max_bs * kMaxSplits * hq;
-  return items * head_dim * sizeof(float) + items * 2 * sizeof(float) + 256;
+  // partial o | partial (m, l) | arrival counters [max_bs][hq] (zero between launches)
+  return items * head_dim * sizeof(float) + items * 2 * sizeof(float) + (size_t)max_bs * hq * sizeof(int) + 256;
 }
 
 namespace b200 {
@@ -346,8 +347,8 @@ int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, c
                      int64_t v_rs, void* k_cache, void* v_cache, const int32_t* out_loc,
                      const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
                      const int32_t* plan, int bs, int hq, int hkv, int64_t num_slots, int page_size,
-                     float scale_log2, void* out, float* part_o, float* part_ml, int dtype,
-                     cudaStream_t st);
+                     float scale_log2, void* out, float* part_o, float* part_ml, int* counters,
+                     int dtype, cudaStream_t st);
 }  // namespace b200
 
 extern "C" int b200_attn_decode(const void* q, int64_t q_row_stride, const void* k,
@@ -376,12 +377,15 @@ extern "C" int b200_attn_decode(const void* q, int64_t q_row_stride, const void*
   const size_t items = (size_t)bs * kMaxSplits * hq;
   float* part_o = reinterpret_cast<float*>(workspace);
   float* part_ml = part_o + items * kD;
+  // arrival counters live at the END of the workspace so that their location does not depend on bs
+  const size_t cnt_bytes = (((size_t)bs * hq * sizeof(int)) + 255) / 256 * 256;
+  int* counters = reinterpret_cast<int*>(static_cast<char*>(workspace) + (workspace_bytes / 256 * 256) - cnt_bytes);
   const float scale_log2 = scale * kLog2e;
   B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "attn_decode: bad dtype %d", dtype);
   if (g_decode_impl.load() == 1)
     return launch_decode_tc(q, q_row_stride, k, k_row_stride, v, v_row_stride, k_cache, v_cache, out_loc,
                             slot_table, slot_table_stride, seq_lens, decode_plan, bs, hq, hkv, num_slots,
-                            page_size, scale_log2, out, part_o, part_ml, dtype, st);
+                            page_size, scale_log2, out, part_o, part_ml, counters, dtype, st);
 #define FILL(T_)                                                                                  \
   DecodeParams<T_> p{(const T_*)q, q_row_stride, (const T_*)k, k_row_stride, (const T_*)v,        \
                      v_row_stride, (T_*)k_cache, (T_*)v_cache, out_loc, slot_table,               \

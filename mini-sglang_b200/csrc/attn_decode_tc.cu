@@ -91,10 +91,12 @@ struct Params {
   int num_slots;
   int box_rows;  // rows per tiled TMA box (8..64, divides page_size); 0 = gather4 mode
   int num_s;     // S^T buffers in use (2..kNumS)
+  int fused_combine;  // 1: last-arriving unit merges the split-KV partials in this launch
   float scale_log2;
   T* out;
   float* part_o;
   float* part_ml;
+  int* counters;  // [bs][hkv] split-KV arrival counters, zero between launches
 };
 
 struct Unit {
@@ -103,20 +105,18 @@ struct Unit {
 };
 static_assert(sizeof(Unit) <= 40, "Unit must fit its smem slot");
 
-__device__ __forceinline__ Unit get_unit(int unit, int hkv, int bs, int chunk_tokens,
-                                         const int32_t* chunk_start, const int32_t* seq_lens) {
+// Work unit `pos` of the size-sorted order (metadata.cu): entry = r | chunk << 16 | n_chunks << 20,
+// the hkv heads of an item are adjacent positions (neighbouring CTAs stream the same token rows).
+__device__ __forceinline__ Unit get_unit(int pos, int hkv, int chunk_tokens, const int32_t* order,
+                                         const int32_t* seq_lens) {
   Unit u;
-  const int cg = unit / hkv;
-  u.h = unit - cg * hkv;
-  int lo = 0, hi = bs;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (chunk_start[mid] <= cg) lo = mid; else hi = mid;
-  }
-  u.r = lo;
-  u.c = cg - chunk_start[lo];
-  u.n_chunks = chunk_start[lo + 1] - chunk_start[lo];
-  u.kv_len = seq_lens[lo];
+  const int item = pos / hkv;
+  u.h = pos - item * hkv;
+  const int e = order[item];
+  u.r = e & 0xffff;
+  u.c = (e >> 16) & 0xf;
+  u.n_chunks = (e >> 20) & 0x1f;
+  u.kv_len = seq_lens[u.r];
   u.kv_begin = u.c * chunk_tokens;
   const int kv_end = min(u.kv_len, u.kv_begin + chunk_tokens);
   u.last_chunk = (u.c == u.n_chunks - 1);
@@ -144,21 +144,30 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
 
   const int chunk_tokens = p.plan[0];
   const int total_units = p.plan[1] * p.hkv;
-  const int32_t* chunk_start = p.plan + kPlanHeader;
+  const int32_t* order = p.plan + kPlanHeader + p.bs + 1;
   const int32_t* seq_lens = p.seq_lens;
+  // This CTA's k-th unit is position k*grid + (k even ? cta : grid-1-cta) of the size-sorted order
+  // ("snake" dealing): per-CTA work is balanced to within about one tile.
+  const int grid = gridDim.x, cta = blockIdx.x;
+  const int n_rounds = (total_units + grid - 1) / grid;
+  auto pos_of = [&](int k) { return k * grid + ((k & 1) ? grid - 1 - cta : cta); };
 
   // ---------------------------------------------------------------- one-time setup
-  // every role walks the same unit list: decode it once (one binary search per thread, in
-  // parallel) instead of once per role per unit
-  for (int i = tid; i < kMaxUnitsSmem; i += kThreads) {
-    const int unit = blockIdx.x + i * gridDim.x;
-    if (unit < total_units)
-      *reinterpret_cast<Unit*>(sUnits + i * 40) = get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
+  // every role walks the same unit list: decode it once, in parallel, into smem
+  for (int k = tid; k < kMaxUnitsSmem && k < n_rounds; k += kThreads) {
+    const int pos = pos_of(k);
+    Unit u;
+    u.n_tiles = -1;  // marks "no unit in this round"
+    if (pos < total_units) u = get_unit(pos, p.hkv, chunk_tokens, order, seq_lens);
+    *reinterpret_cast<Unit*>(sUnits + k * 40) = u;
   }
-  auto unit_at = [&](int unit) {
-    const int i = (unit - (int)blockIdx.x) / (int)gridDim.x;
-    if (i < kMaxUnitsSmem) return *reinterpret_cast<const Unit*>(sUnits + i * 40);
-    return get_unit(unit, p.hkv, p.bs, chunk_tokens, chunk_start, seq_lens);
+  auto unit_at = [&](int k) {
+    if (k < kMaxUnitsSmem) return *reinterpret_cast<const Unit*>(sUnits + k * 40);
+    const int pos = pos_of(k);
+    Unit u;
+    u.n_tiles = -1;
+    if (pos < total_units) u = get_unit(pos, p.hkv, chunk_tokens, order, seq_lens);
+    return u;
   };
   // zero the operand buffers whose padding rows (heads >= G) are never written again
   for (int i = tid; i < (2 * kQBufBytes + 2 * kPBufBytes) / 16; i += kThreads)
@@ -205,8 +214,9 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
       const int full0 = kind == 0 ? kFullK : kFullV, empty0 = kind == 0 ? kEmptyK : kEmptyV;
       const uint32_t ring = sbase + (kind == 0 ? Smem::kring : Smem::vring);
       uint32_t tile_count = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const Unit u = unit_at(unit);
+      for (int k = 0; k < n_rounds; ++k) {
+        const Unit u = unit_at(k);
+        if (u.n_tiles <= 0) continue;
         const int32_t* slots = p.slot_table + (int64_t)u.r * p.st_stride;
         const int col0 = u.h * kD;
         // four slots of row group `grp` (rows 4*grp..4*grp+3 of tile t); invalid rows -> out of range
@@ -275,17 +285,17 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
       // unit boundaries) ahead of PV, so K tiles are consumed -- and their ring slots recycled -- as
       // soon as they land, independent of the softmax latency.
       struct Cursor {
-        int unit;        // current unit id (grid-strided)
+        int k;           // round = index into this CTA's unit list
         int j;           // tile within the unit
         int n_tiles;     // tiles of the current unit
         uint32_t tc;     // global tile counter
         uint32_t uc;     // global counter of units with tiles
       };
       auto seek = [&](Cursor& c) {  // position on the next unit that has tiles
-        while (c.unit < total_units) {
-          c.n_tiles = unit_at(c.unit).n_tiles;
+        while (c.k < n_rounds) {
+          c.n_tiles = unit_at(c.k).n_tiles;
           if (c.n_tiles > 0) return;
-          c.unit += gridDim.x;
+          ++c.k;
         }
         c.n_tiles = 0;
       };
@@ -294,18 +304,18 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
         if (++c.j == c.n_tiles) {
           c.j = 0;
           ++c.uc;
-          c.unit += gridDim.x;
+          ++c.k;
           seek(c);
         }
       };
-      Cursor qk{(int)blockIdx.x, 0, 0, 0, 0}, pv{(int)blockIdx.x, 0, 0, 0, 0};
+      Cursor qk{0, 0, 0, 0, 0}, pv{0, 0, 0, 0, 0};
       seek(qk);
       seek(pv);
       uint32_t spins = 0;
-      while (pv.unit < total_units) {
+      while (pv.k < n_rounds) {
         bool progress = false;
         // ---- S^T[tile] = K_tile . Q^T
-        if (qk.unit < total_units && qk.tc - pv.tc < (uint32_t)p.num_s) {
+        if (qk.k < n_rounds && qk.tc - pv.tc < (uint32_t)p.num_s) {
           const uint32_t tc = qk.tc, stage = tc % kStages, qb = qk.uc & 1;
           if (mbar_test_wait(bar(kFullK + stage), (tc / kStages) & 1) &&
               (qk.j > 0 || mbar_test_wait(bar(kQFull + qb), (qk.uc >> 1) & 1))) {
@@ -356,9 +366,9 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
   } else if (warp == kWarpQ) {
     // ============================================================ Q loader
     uint32_t unit_count = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      const Unit u = unit_at(unit);
-      if (u.n_tiles == 0) continue;
+    for (int k = 0; k < n_rounds; ++k) {
+      const Unit u = unit_at(k);
+      if (u.n_tiles <= 0) continue;
       const uint32_t qb = unit_count & 1;
       mbar_wait(bar(kQEmpty + qb), ((unit_count >> 1) & 1) ^ 1);
       uint8_t* qdst = smem + Smem::qbuf + qb * kQBufBytes;
@@ -382,8 +392,9 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     float* red_sum = red + 2 * 4 * 16; // [4][16]
     float* red_new = red_sum + 4 * 16; // [4][16]
     uint32_t tile_count = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      const Unit u = unit_at(unit);
+    for (int k = 0; k < n_rounds; ++k) {
+      const Unit u = unit_at(k);
+      if (u.n_tiles < 0) continue;  // no unit for this CTA in the last round
       float acc[G], l_thr[G], m_run[G], alpha_prev[G], q_new[G];
       float kn = 0.f, vn = 0.f;
 #pragma unroll
@@ -531,6 +542,38 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
           p.part_ml[(base + ct) * 2 + 0] = mm;
           p.part_ml[(base + ct) * 2 + 1] = ll;
         }
+        // ---- fused split-KV combine: the unit that arrives last for (request, kv head) merges
+        // all partials (flash-decoding reduction) -- no second launch, no grid-wide wait.
+        if (!p.fused_combine) continue;
+        __threadfence();            // our partials are visible device-wide before we count in
+        named_bar_sync(1, 128);
+        int* flag = reinterpret_cast<int*>(red_new);
+        if (ct == 0) {
+          const int old = atomicAdd(p.counters + u.r * p.hkv + u.h, 1);
+          *flag = (old == u.n_chunks - 1);
+          if (old == u.n_chunks - 1) p.counters[u.r * p.hkv + u.h] = 0;  // leave it zero for the next launch
+        }
+        named_bar_sync(1, 128);
+        const bool is_last = *flag != 0;
+        named_bar_sync(1, 128);     // flag (aliases red_new) is reused by the next unit
+        if (is_last) {
+          __threadfence();          // acquire: the other chunks' partials
+          const int64_t b0 = ((int64_t)u.r * kMaxSplits) * p.hq + u.h * G;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            float mx = -INFINITY;
+            for (int c = 0; c < u.n_chunks; ++c)
+              mx = fmaxf(mx, __ldcg(p.part_ml + (b0 + (int64_t)c * p.hq + g) * 2));
+            float o = 0.f, l = 0.f;
+            for (int c = 0; c < u.n_chunks; ++c) {
+              const int64_t idx = b0 + (int64_t)c * p.hq + g;
+              const float w = fast_exp2(__ldcg(p.part_ml + idx * 2) - mx);
+              l += w * __ldcg(p.part_ml + idx * 2 + 1);
+              o += w * __ldcg(p.part_o + idx * kD + ct);
+            }
+            p.out[((int64_t)u.r * p.hq + u.h * G + g) * kD + ct] = DTypeTraits<T>::from_float(o / l);
+          }
+        }
       }
     }
   }
@@ -556,8 +599,10 @@ static int launch_g(const Params<T>& p, const CUtensorMap& mk, const CUtensorMap
   }
   attn_decode_tc_kernel<T, G><<<num_sms(), kThreads, smem, st>>>(p, mk, mv, bk, bv);
   B200_POST_LAUNCH();
-  attn_combine_kernel<T><<<dim3(p.bs, p.hq), kHeadDim, 0, st>>>(p.part_o, p.part_ml, p.plan, p.hq, p.out);
-  B200_POST_LAUNCH();
+  if (!p.fused_combine) {
+    attn_combine_kernel<T><<<dim3(p.bs, p.hq), kHeadDim, 0, st>>>(p.part_o, p.part_ml, p.plan, p.hq, p.out);
+    B200_POST_LAUNCH();
+  }
   return 0;
 }
 
@@ -591,14 +636,15 @@ static int launch(const Params<T>& p, cudaStream_t st) {
 }  // namespace dtc
 
 extern std::atomic<int> g_decode_lookahead;
+extern std::atomic<int> g_decode_fused_combine;
 
 // entry used by b200_attn_decode (attn_decode.cu)
 int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, const void* v,
                      int64_t v_rs, void* k_cache, void* v_cache, const int32_t* out_loc,
                      const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
                      const int32_t* plan, int bs, int hq, int hkv, int64_t num_slots, int page_size,
-                     float scale_log2, void* out, float* part_o, float* part_ml, int dtype,
-                     cudaStream_t st) {
+                     float scale_log2, void* out, float* part_o, float* part_ml, int* counters,
+                     int dtype, cudaStream_t st) {
   int num_s = g_decode_lookahead.load();
   if (num_s < 2) num_s = 2;
   if (num_s > dtc::kNumS) num_s = dtc::kNumS;
@@ -616,7 +662,8 @@ int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, c
 #define RUN(T_)                                                                                   \
   dtc::Params<T_> p{(const T_*)q, q_rs, (const T_*)k, k_rs, (const T_*)v, v_rs, (T_*)k_cache,     \
                     (T_*)v_cache, out_loc, slot_table, st_stride, seq_lens, plan, bs, hq, hkv,    \
-                    (int)num_slots, box_rows, num_s, scale_log2, (T_*)out, part_o, part_ml};                       \
+                    (int)num_slots, box_rows, num_s, g_decode_fused_combine.load(), scale_log2, (T_*)out,  \
+                    part_o, part_ml, counters};                       \
   return dtc::launch<T_>(p, st)
   if (dtype == B200_DTYPE_BF16) {
     RUN(__nv_bfloat16);

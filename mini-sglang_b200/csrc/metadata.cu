@@ -10,6 +10,7 @@ namespace b200 {
 
 constexpr int kPlanHeader = 4;  // {chunk_tokens, total_chunks, bs, reserved}
 constexpr int kMaxSplits = 16;  // chunks per request never exceed this (workspace sizing)
+constexpr int kOrderBins = 128; // counting-sort bins (tiles per work item, clamped)
 
 // ---- row snapshot: slot_table[r][0:width] = page_table[table_idx_r][0:width]
 __global__ void __launch_bounds__(256) meta_rows_kernel(const int32_t* __restrict__ req_info,
@@ -99,15 +100,15 @@ __global__ void __launch_bounds__(1024) meta_scan_kernel(const int32_t* __restri
   }
   __syncthreads();
   if (plan == nullptr) return;
-  // chunk size: aim at `target_items` (request, chunk) items, tiles of 64 tokens,
+  // chunk size: aim at `target_items` (request, chunk) items, whole tiles of 128 tokens,
   // never more than kMaxSplits chunks per request.
   const int total_kv = carry_k;
   const int max_kv = s_max;
   int chunk = (total_kv + target_items - 1) / target_items;
   const int min_chunk = (max_kv + kMaxSplits - 1) / kMaxSplits;
   if (chunk < min_chunk) chunk = min_chunk;
-  chunk = ((chunk + 63) / 64) * 64;
-  if (chunk < 64) chunk = 64;
+  chunk = ((chunk + 127) / 128) * 128;  // whole 128-token tiles
+  if (chunk < 128) chunk = 128;
   int carry_c = 0;
   for (int base = 0; base < bs; base += 1024) {
     const int r = base + tid;
@@ -125,11 +126,52 @@ __global__ void __launch_bounds__(1024) meta_scan_kernel(const int32_t* __restri
     plan[3] = 0;
     plan[kPlanHeader] = 0;
   }
+  // ---- work order: (request, chunk) items sorted by size, largest first (counting sort on the
+  // number of 128-token tiles).  The decode kernel deals them to its persistent CTAs in snake
+  // order, which balances the per-CTA work to within about one tile.
+  // entry = r | chunk_idx << 16 | n_chunks << 20   (r < 65536, chunk_idx < 16, n_chunks <= 16)
+  __shared__ int hist[kOrderBins];
+  for (int i = tid; i < kOrderBins; i += 1024) hist[i] = 0;
+  __syncthreads();
+  int32_t* order = plan + kPlanHeader + bs + 1;
+  auto tiles_of = [&](int kl, int nc, int c) {
+    int len = min(chunk, kl - c * chunk);
+    if (c == nc - 1) len -= 1;  // the appended token is not part of the tiled range
+    int t = (len + 127) / 128;
+    return t < kOrderBins - 1 ? t : kOrderBins - 1;
+  };
+  for (int r = tid; r < bs; r += 1024) {
+    const int kl = req_info[3 * r + 2];
+    const int nc = (kl + chunk - 1) / chunk;
+    for (int c = 0; c < nc; ++c) atomicAdd(&hist[tiles_of(kl, nc, c)], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {  // descending exclusive prefix: largest items first
+    int run = 0;
+    for (int b = kOrderBins - 1; b >= 0; --b) {
+      const int n = hist[b];
+      hist[b] = run;
+      run += n;
+    }
+  }
+  __syncthreads();
+  for (int r = tid; r < bs; r += 1024) {
+    const int kl = req_info[3 * r + 2];
+    const int nc = (kl + chunk - 1) / chunk;
+    for (int c = 0; c < nc; ++c) {
+      const int pos = atomicAdd(&hist[tiles_of(kl, nc, c)], 1);
+      order[pos] = r | (c << 16) | (nc << 20);
+    }
+  }
 }
 
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" size_t b200_decode_plan_ints(int bs) {
+  return (size_t)kPlanHeader + (size_t)bs + 1 + (size_t)kMaxSplits * bs;
+}
 
 extern "C" int b200_build_metadata(const int32_t* req_info, int bs, const int32_t* page_table,
                                    int64_t page_table_stride, int32_t* seq_lens,
@@ -137,7 +179,7 @@ extern "C" int b200_build_metadata(const int32_t* req_info, int bs, const int32_
                                    int32_t* slot_table, int64_t slot_table_stride, int width,
                                    int32_t* decode_plan, int num_kv_heads, int num_ctas_hint,
                                    void* stream) {
-  B200_CHECK_ARG(bs > 0, "build_metadata: empty batch");
+  B200_CHECK_ARG(bs > 0 && bs < 65536, "build_metadata: batch size %d out of range [1, 65535]", bs);
   B200_CHECK_ARG(width >= 0 && width <= page_table_stride && width <= slot_table_stride,
                  "build_metadata: width %d exceeds a table stride (%lld / %lld)", width,
                  (long long)page_table_stride, (long long)slot_table_stride);
