@@ -12,6 +12,7 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a)")
+    config.addinivalue_line("markers", "slow: long-running CPU test")
 
 
 @pytest.fixture(scope="session")
