@@ -43,6 +43,7 @@ B200_API uint64_t b200_launch_count(void);
 B200_API int b200_device_supported(void);
 /* Kernel selection knobs (debug / cross-checking only; defaults are the product path):
  *   "decode_impl": 1 = tcgen05 + TMA kernel (default), 0 = cp.async / CUDA-core kernel.
+ *   "prefill_impl": 1 = tcgen05 kernel (default, needs prefill_plan), 0 = mma.sync bring-up kernel.
  *   "decode_lookahead": S^T buffers the UMMA issuer may run ahead (2..4, default 4).
  *   "decode_fused_combine": 1 = merge split-KV partials inside the decode launch, 0 = combine kernel (default).
  * Returns the previous value, or -1 for an unknown name. */
@@ -120,6 +121,13 @@ B200_API int b200_build_metadata(const int32_t* req_info, int bs, const int32_t*
                         int width, int32_t* decode_plan, int num_kv_heads, int num_ctas_hint,
                         void* stream);
 
+/* Prefill work list for b200_attn_prefill: prefill_plan[4 + capacity_items] =
+ * {n_items, 0, 0, 0, item[...]}, item = r | q_tile << 16 for every 128-row query tile of every
+ * request, heaviest (most KV tiles under the causal mask) first.  capacity_items must be
+ * >= sum_r ceil(q_len_r / 128) (<= nnz / 128 + bs); n_items = -1 reports an undersized buffer. */
+B200_API int b200_build_prefill_plan(const int32_t* req_info, int bs, int32_t* prefill_plan,
+                                     int capacity_items, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * a1  Attention forward.  Replace BaseAttnBackend.forward (M/attention/base.py:20-22; impls
  *     fi.py:176-188, fa.py:49-65, trtllm.py:49-89): append k,v at out_loc, then causal
@@ -151,12 +159,15 @@ B200_API int b200_attn_decode(const void* q, int64_t q_row_stride, const void* k
 
 /* Prefill / extend: ragged query rows, cu_seqlens_q[bs+1]; request r has
  * q_len = cu_seqlens_q[r+1]-cu_seqlens_q[r] new tokens at kv positions
- * [seq_lens[r]-q_len, seq_lens[r]).  max_seqlen_q is a host-side upper bound (grid sizing). */
+ * [seq_lens[r]-q_len, seq_lens[r]).  max_seqlen_q is a host-side upper bound (grid sizing).
+ * prefill_plan: b200_build_prefill_plan output (work list of the tcgen05 kernel); NULL selects
+ * the mma.sync bring-up kernel (as does b200_set_option("prefill_impl", 0)). */
 B200_API int b200_attn_prefill(const void* q, int64_t q_row_stride, const void* k, int64_t k_row_stride,
                       const void* v, int64_t v_row_stride, void* k_cache, void* v_cache,
                       int64_t num_slots, int page_size, const int32_t* out_loc, const int32_t* slot_table,
                       int64_t slot_table_stride, const int32_t* seq_lens,
-                      const int32_t* cu_seqlens_q, int bs, int64_t nnz, int max_seqlen_q, int hq,
+                      const int32_t* cu_seqlens_q, const int32_t* prefill_plan, int bs, int64_t nnz,
+                      int max_seqlen_q, int hq,
                       int hkv, int head_dim, float scale, void* out, void* workspace,
                       size_t workspace_bytes, int dtype, void* stream);
 

@@ -14,7 +14,7 @@ from typing import Optional
 _LIB: Optional[C.CDLL] = None
 LIB_PATH = Path(__file__).resolve().parent / "libb200attn.so"
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _i32, _i64, _f32, _vp, _sz = C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
 
@@ -40,6 +40,7 @@ SIGNATURES = {
         [_vp, _vp, _vp, _vp, _f32, _vp, _i32, _vp, _i64, _i32, _i32, _i32, _i64, _i64, _i32, _vp],
     ),
     "b200_decode_plan_ints": (_sz, [_i32]),
+    "b200_build_prefill_plan": (_i32, [_vp, _i32, _vp, _i32, _vp]),
     "b200_build_metadata": (
         _i32,
         [_vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp],
@@ -52,7 +53,7 @@ SIGNATURES = {
     ),
     "b200_attn_prefill": (
         _i32,
-        [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp]
+        [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp]
         + [_i32, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _i32, _vp],
     ),
 }

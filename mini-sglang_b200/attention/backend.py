@@ -87,6 +87,7 @@ class B200Metadata(BaseAttnMetadata):
     decode_plan: torch.Tensor  # int32 [4 + bs + 1 + 16 bs] split-KV plan (see include/b200attn.h)
     small_block: torch.Tensor  # the contiguous buffer the four small tensors are views of
     bs: int
+    prefill_plan: Optional[torch.Tensor] = None  # int32 work list of the prefill kernel (q_len > 1)
 
     def get_last_indices(self, bs: int) -> torch.Tensor:
         return self.cu_seqlens_q[1 : 1 + bs] - 1
@@ -177,6 +178,17 @@ class B200AttnBackend(BaseAttnBackend):
             ),
             "b200_build_metadata",
         )
+        prefill_plan = None
+        if max_q > 1:
+            cap = (len(flat) // 3) + sum(r.extend_len for r in reqs) // 128
+            prefill_plan = torch.empty(4 + cap, dtype=torch.int32, device=dev)
+            _cabi.check(
+                self._lib.b200_build_prefill_plan(
+                    info.data_ptr(), bs, prefill_plan.data_ptr(), cap,
+                    torch.cuda.current_stream(dev).cuda_stream,
+                ),
+                "b200_build_prefill_plan",
+            )
         batch.attn_metadata = B200Metadata(
             cu_seqlens_k=cu_k,
             cu_seqlens_q=cu_q,
@@ -187,6 +199,7 @@ class B200AttnBackend(BaseAttnBackend):
             decode_plan=plan,
             small_block=small,
             bs=bs,
+            prefill_plan=prefill_plan,
         )
 
     # ------------------------------------------------------------------ forward
@@ -238,7 +251,9 @@ class B200AttnBackend(BaseAttnBackend):
                     v2.stride(0), kc.data_ptr(), vc.data_ptr(), num_slots, self.page_size,
                     out_loc.data_ptr(),
                     md.page_table.data_ptr(), md.page_table.stride(0), md.cache_seqlens.data_ptr(),
-                    md.cu_seqlens_q.data_ptr(), md.bs, nnz, md.max_seqlen_q, hq, hkv, d, self.scale,
+                    md.cu_seqlens_q.data_ptr(),
+                    md.prefill_plan.data_ptr() if md.prefill_plan is not None else None,
+                    md.bs, nnz, md.max_seqlen_q, hq, hkv, d, self.scale,
                     out.data_ptr(), ws.data_ptr(), ws.numel(), dtype, stream,
                 ),
                 "b200_attn_prefill",

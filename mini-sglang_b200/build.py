@@ -27,6 +27,7 @@ SOURCES = [
     "attn_decode_tc.cu",
     "tma_host.cu",
     "attn_prefill.cu",
+    "attn_prefill_tc.cu",
 ]
 
 NVCC_FLAGS = [

@@ -320,6 +320,15 @@ static int launch_prefill(const PrefillParams<T>& p, int max_q, cudaStream_t st)
 
 }  // namespace b200
 
+namespace b200 {
+extern std::atomic<int> g_prefill_impl;
+int launch_prefill_tc(const void* q, int64_t q_rs, int64_t nnz, const void* k_cache, const void* v_cache,
+                      const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
+                      const int32_t* cu_q, const int32_t* prefill_plan, int bs, int hq, int hkv,
+                      int64_t num_slots, int page_size, float scale_log2, void* out, int dtype,
+                      cudaStream_t st);
+}  // namespace b200
+
 using namespace b200;
 
 extern "C" int b200_attn_prefill(const void* q, int64_t q_row_stride, const void* k,
@@ -327,13 +336,12 @@ extern "C" int b200_attn_prefill(const void* q, int64_t q_row_stride, const void
                                  void* k_cache, void* v_cache, int64_t num_slots, int page_size,
                                  const int32_t* out_loc, const int32_t* slot_table,
                                  int64_t slot_table_stride,
-                                 const int32_t* seq_lens, const int32_t* cu_seqlens_q, int bs,
-                                 int64_t nnz, int max_seqlen_q, int hq, int hkv, int head_dim,
+                                 const int32_t* seq_lens, const int32_t* cu_seqlens_q,
+                                 const int32_t* prefill_plan, int bs, int64_t nnz, int max_seqlen_q,
+                                 int hq, int hkv, int head_dim,
                                  float scale, void* out, void* workspace, size_t workspace_bytes,
                                  int dtype, void* stream) {
   (void)workspace;
-  (void)num_slots;
-  (void)page_size;
   (void)workspace_bytes;
   B200_CHECK_ARG(head_dim == kD, "attn_prefill: head_dim must be 128 (got %d)", head_dim);
   B200_CHECK_ARG(bs > 0 && hq > 0 && hkv > 0 && hq % hkv == 0,
@@ -355,6 +363,10 @@ extern "C" int b200_attn_prefill(const void* q, int64_t q_row_stride, const void
     return rc;
   auto st = (cudaStream_t)stream;
   const float scale_log2 = scale * kLog2e;
+  if (prefill_plan != nullptr && g_prefill_impl.load() == 1 && (hq / hkv) <= 16)
+    return launch_prefill_tc(q, q_row_stride, nnz, k_cache, v_cache, slot_table, slot_table_stride,
+                             seq_lens, cu_seqlens_q, prefill_plan, bs, hq, hkv, num_slots, page_size,
+                             scale_log2, out, dtype, st);
   if (dtype == B200_DTYPE_BF16) {
     PrefillParams<__nv_bfloat16> p{(const __nv_bfloat16*)q, q_row_stride,
                                    (const __nv_bfloat16*)k_cache, (const __nv_bfloat16*)v_cache,

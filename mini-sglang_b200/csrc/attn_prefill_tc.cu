@@ -1,0 +1,508 @@
+// Blackwell-native ragged prefill / extend attention: TMA -> swizzled smem -> tcgen05 UMMA with
+// S, P and O resident in TMEM (replaces BatchPrefillWithPagedKVCacheWrapper.run,
+// python/minisgl/attention/fi.py:150-165,188; causal, bottom-right aligned).
+//
+// Compute-bound: exact causal flops = 4*Hq*D*sum_r[q*cached + q(q+1)/2].
+// Persistent, one CTA per SM, 384 threads.  A work unit is (request, 128-row query tile, kv head,
+// pair of query heads of that kv head's GQA group): the two heads ("sub-tiles" A and B) share every
+// K/V tile, so K/V bytes per flop are halved and two softmax warpgroups ping-pong against one
+// tensor pipe (FlashAttention-4 style):
+//
+//   warp 0      K producer (+ the unit's Q sub-tiles): TMA boxes per page piece / gather4 rows
+//   warp 1      V producer
+//   warp 2      UMMA issuer (one thread) + TMEM allocation
+//                 S_s = Q_s . K^T            (A, B from smem, K-major, 128B swizzle)  128x128 fp32
+//                 O_s += P_s . V             (A = P_s from TMEM, B = V tile MN-major)  128x128 fp32
+//               issue order per KV tile j:  PV_A(j) QK_A(j+1) PV_B(j) QK_B(j+1)  (in-order tensor pipe)
+//   warps 4-7   softmax warpgroup A, warps 8-11 softmax warpgroup B: thread i owns query row i
+//               (TMEM lane i): row max / exp2 / row sum with no cross-thread traffic, P written back
+//               to TMEM as packed bf16 over the S columns, O rescaled in TMEM only when the running
+//               max moved by more than 2^8 (lazy correction), final O/l -> bf16 -> global.
+// TMEM: S_A 0..127 (P_A aliases 0..63), S_B 128..255, O_A 256..383, O_B 384..511.
+// The KV append of the new rows is done by the store kernel issued in front by the same C call.
+#include "b200attn.h"
+#include "common.cuh"
+#include "sm100.cuh"
+
+#include <type_traits>
+
+namespace b200 {
+
+int get_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, bool is_bf16);
+
+namespace ptc {
+
+using namespace sm100;
+
+constexpr int kD = 128;
+constexpr int kBM = 128;                   // query rows per sub-tile
+constexpr int kBN = 128;                   // keys per tile
+constexpr int kStages = 2;                 // K ring depth = V ring depth
+constexpr int kThreads = 384;
+constexpr int kHalfBytes = 128 * 128;      // [128 rows x 64 cols] bf16, 128B-swizzled: 16 KB
+constexpr int kTileBytes = 2 * kHalfBytes; // 32 KB
+constexpr int kMaxUnitsSmem = 64;
+constexpr int kTmemCols = 512;
+constexpr float kRescaleThreshold = 8.0f;  // log2 domain
+
+struct Smem {
+  static constexpr int q = 0;                              // 2 sub-tiles x 32 KB
+  static constexpr int kring = 2 * kTileBytes;             // kStages x 32 KB
+  static constexpr int vring = kring + kStages * kTileBytes;
+  static constexpr int bars = vring + kStages * kTileBytes;  // 16 mbarriers
+  static constexpr int tmem_ptr = bars + 16 * 8;
+  static constexpr int units = tmem_ptr + 16;
+  static constexpr int total = units + kMaxUnitsSmem * 48;
+};
+enum Bar { kFullK = 0, kEmptyK = 2, kFullV = 4, kEmptyV = 6, kQFull = 8, kQEmpty = 9, kSFull = 10, kPFull = 12, kOFull = 14 };
+
+template <typename T>
+struct Params {
+  const int32_t* slot_table;
+  int64_t st_stride;
+  const int32_t* seq_lens;
+  const int32_t* cu_q;
+  const int32_t* plan;  // {n_items, 0,0,0, item[...]}
+  int bs, hq, hkv;
+  int num_slots;
+  int box_rows;
+  float scale_log2;
+  T* out;
+};
+
+struct Unit {
+  int r, q_start, q_len, q_begin, kv_len, cached, kv_hi, n_tiles, h, head0, n_sub;
+};
+static_assert(sizeof(Unit) <= 48, "Unit must fit its smem slot");
+
+__device__ __forceinline__ Unit get_unit(int pos, int hkv, int group, const int32_t* items,
+                                         const int32_t* seq_lens, const int32_t* cu_q) {
+  Unit u;
+  const int n_pairs = (group + 1) >> 1;
+  const int per_item = hkv * n_pairs;
+  const int item = pos / per_item;
+  const int rem = pos - item * per_item;
+  u.h = rem / n_pairs;
+  const int pair = rem - u.h * n_pairs;
+  const int e = items[item];
+  u.r = e & 0xffff;
+  u.q_start = ((e >> 16) & 0xffff) * kBM;
+  u.q_begin = cu_q[u.r];
+  u.q_len = cu_q[u.r + 1] - u.q_begin;
+  u.kv_len = seq_lens[u.r];
+  u.cached = u.kv_len - u.q_len;
+  u.kv_hi = min(u.kv_len, u.cached + min(u.q_len, u.q_start + kBM));
+  u.n_tiles = (u.kv_hi + kBN - 1) / kBN;
+  u.head0 = u.h * group + pair * 2;
+  u.n_sub = min(2, group - pair * 2);
+  return u;
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  typename DTypeTraits<T>::T2 v = DTypeTraits<T>::from_float2(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map_q,
+                       const __grid_constant__ CUtensorMap map_k,
+                       const __grid_constant__ CUtensorMap map_v,
+                       const __grid_constant__ CUtensorMap box_k,
+                       const __grid_constant__ CUtensorMap box_v) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid / kWarp, lane = tid % kWarp;
+  auto bar = [&](int i) { return sbase + Smem::bars + i * 8; };
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + Smem::tmem_ptr);
+  uint8_t* sUnits = smem + Smem::units;
+
+  const int group = p.hq / p.hkv;
+  const int n_pairs = (group + 1) >> 1;
+  const int total_units = p.plan[0] * p.hkv * n_pairs;
+  const int32_t* items = p.plan + 4;
+  const int grid = gridDim.x, cta = blockIdx.x;
+  const int n_rounds = (total_units + grid - 1) / grid;
+  auto pos_of = [&](int k) { return k * grid + ((k & 1) ? grid - 1 - cta : cta); };
+
+  // ---------------------------------------------------------------- one-time setup
+  for (int k = tid; k < kMaxUnitsSmem && k < n_rounds; k += kThreads) {
+    const int pos = pos_of(k);
+    Unit u;
+    u.n_tiles = -1;
+    if (pos < total_units) u = get_unit(pos, p.hkv, group, items, p.seq_lens, p.cu_q);
+    *reinterpret_cast<Unit*>(sUnits + k * 48) = u;
+  }
+  auto unit_at = [&](int k) {
+    if (k < kMaxUnitsSmem) return *reinterpret_cast<const Unit*>(sUnits + k * 48);
+    const int pos = pos_of(k);
+    Unit u;
+    u.n_tiles = -1;
+    if (pos < total_units) u = get_unit(pos, p.hkv, group, items, p.seq_lens, p.cu_q);
+    return u;
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar(kFullK + s), 1);
+      mbar_init(bar(kEmptyK + s), 1);
+      mbar_init(bar(kFullV + s), 1);
+      mbar_init(bar(kEmptyV + s), 1);
+    }
+    mbar_init(bar(kQFull), 1);
+    mbar_init(bar(kQEmpty), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(kSFull + s), 1);
+      mbar_init(bar(kPFull + s), 128);
+      mbar_init(bar(kOFull + s), 1);
+    }
+    fence_barrier_init();
+    prefetch_tensormap(&map_q);
+    prefetch_tensormap(&map_k);
+    prefetch_tensormap(&map_v);
+    prefetch_tensormap(&box_k);
+    prefetch_tensormap(&box_v);
+  }
+  if (warp == 2) tmem_alloc(sbase + Smem::tmem_ptr, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp < 2) {
+    // ============================================================ TMA producers: warp 0 = K (+Q), warp 1 = V
+    const int kind = warp;
+    const int rb = p.box_rows;
+    const CUtensorMap* gmap = kind == 0 ? &map_k : &map_v;
+    const CUtensorMap* bmap = kind == 0 ? &box_k : &box_v;
+    const int full0 = kind == 0 ? kFullK : kFullV, empty0 = kind == 0 ? kEmptyK : kEmptyV;
+    const uint32_t ring = sbase + (kind == 0 ? Smem::kring : Smem::vring);
+    uint32_t tile_count = 0, unit_count = 0;
+    for (int k = 0; k < n_rounds; ++k) {
+      const Unit u = unit_at(k);
+      if (u.n_tiles <= 0) continue;
+      const int32_t* slots = p.slot_table + (int64_t)u.r * p.st_stride;
+      const int col0 = u.h * kD;
+      if (kind == 0) {
+        // the unit's query sub-tiles (rows past the tensor end are zero filled, rows past the
+        // request's end belong to the next request: computed, never stored)
+        mbar_wait(bar(kQEmpty), (unit_count & 1) ^ 1);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(bar(kQFull), (uint32_t)u.n_sub * kTileBytes);
+          for (int s = 0; s < u.n_sub; ++s)
+            for (int half = 0; half < 2; ++half)
+              tma_load_2d(sbase + Smem::q + s * kTileBytes + half * kHalfBytes, &map_q, bar(kQFull),
+                          (u.head0 + s) * kD + half * 64, u.q_begin + u.q_start);
+        }
+        __syncwarp();
+      }
+      ++unit_count;
+      for (int t = 0; t < u.n_tiles; ++t, ++tile_count) {
+        const uint32_t stage = tile_count % kStages, phase = (tile_count / kStages) & 1;
+        const int tile_begin = t * kBN;
+        if (rb > 0) {
+          const int n_instr = (kBN / rb) * 2;
+          const int box = lane >> 1, half = lane & 1;
+          const int pb = tile_begin + box * rb;
+          int first_slot = p.num_slots;
+          if (lane < n_instr && pb < u.kv_hi) first_slot = __ldg(slots + pb);
+          mbar_wait(bar(empty0 + stage), phase ^ 1);
+          if (lane == 0) mbar_arrive_expect_tx(bar(full0 + stage), kTileBytes);
+          __syncwarp();
+          if (lane < n_instr)
+            tma_load_2d(ring + stage * kTileBytes + half * kHalfBytes + box * rb * 128, bmap,
+                        bar(full0 + stage), col0 + half * 64, first_slot);
+        } else {
+          // gather mode: 32 row groups x 2 halves = 2 gather4 per lane
+          int4 rr[2];
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int grp = (lane >> 1) + it * 16;
+            const int pos0 = tile_begin + grp * 4;
+            if (pos0 + 3 < u.kv_hi) {
+              rr[it] = __ldg(reinterpret_cast<const int4*>(slots + pos0));
+            } else {
+              rr[it].x = pos0 + 0 < u.kv_hi ? __ldg(slots + pos0 + 0) : p.num_slots;
+              rr[it].y = pos0 + 1 < u.kv_hi ? __ldg(slots + pos0 + 1) : p.num_slots;
+              rr[it].z = pos0 + 2 < u.kv_hi ? __ldg(slots + pos0 + 2) : p.num_slots;
+              rr[it].w = pos0 + 3 < u.kv_hi ? __ldg(slots + pos0 + 3) : p.num_slots;
+            }
+          }
+          mbar_wait(bar(empty0 + stage), phase ^ 1);
+          if (lane == 0) mbar_arrive_expect_tx(bar(full0 + stage), kTileBytes);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int grp = (lane >> 1) + it * 16, half = lane & 1;
+            tma_gather4(ring + stage * kTileBytes + half * kHalfBytes + grp * 512, gmap, bar(full0 + stage),
+                        col0 + half * 64, rr[it].x, rr[it].y, rr[it].z, rr[it].w);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ============================================================ UMMA issuer (one thread)
+    if (lane == 0) {
+      constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, kBf16, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, 128, kBf16, false, true);  // B = V, MN-major
+      uint32_t tile_count = 0, unit_count = 0;
+      uint32_t p_count[2] = {0, 0};  // P tiles consumed per sub-tile (phase of kPFull)
+      auto qk = [&](int s, uint32_t tc) {
+        const uint32_t kb = sbase + Smem::kring + (tc % kStages) * kTileBytes;
+        const uint32_t qa = sbase + Smem::q + s * kTileBytes;
+        const uint32_t d = tmem_base + s * 128;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = make_smem_desc(qa + (kk >> 2) * kHalfBytes + (kk & 3) * 32, 16, 1024, kLayoutSW128);
+          const uint64_t db = make_smem_desc(kb + (kk >> 2) * kHalfBytes + (kk & 3) * 32, 16, 1024, kLayoutSW128);
+          umma_f16_ss(d, da, db, idesc_qk, kk > 0);
+        }
+        umma_commit(bar(kSFull + s));
+      };
+      auto pv = [&](int s, uint32_t tc, bool first) {
+        mbar_wait(bar(kPFull + s), p_count[s] & 1);
+        ++p_count[s];
+        tc_fence_after_sync();
+        const uint32_t vb = sbase + Smem::vring + (tc % kStages) * kTileBytes;
+        const uint32_t pa = tmem_base + s * 128;          // packed bf16 P over the S columns
+        const uint32_t d = tmem_base + 256 + s * 128;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          // B = V (MN-major): 16 keys = two 8-key swizzle atoms (1024 B each); dims 64..127 at +16 KB
+          const uint64_t db = make_smem_desc(vb + kk * 2048, kHalfBytes, 1024, kLayoutSW128);
+          umma_f16_ts(d, pa + kk * 8, db, idesc_pv, (!first) || kk > 0);
+        }
+        umma_commit(bar(kOFull + s));
+      };
+      for (int k = 0; k < n_rounds; ++k) {
+        const Unit u = unit_at(k);
+        if (u.n_tiles <= 0) continue;
+        mbar_wait(bar(kQFull), unit_count & 1);
+        ++unit_count;
+        // tile 0: scores of both sub-tiles
+        mbar_wait(bar(kFullK + tile_count % kStages), (tile_count / kStages) & 1);
+        tc_fence_after_sync();
+        for (int s = 0; s < u.n_sub; ++s) qk(s, tile_count);
+        umma_commit(bar(kEmptyK + tile_count % kStages));
+        if (u.n_tiles == 1) umma_commit(bar(kQEmpty));
+        for (int j = 0; j < u.n_tiles; ++j) {
+          const uint32_t tc = tile_count + j;
+          const bool more = j + 1 < u.n_tiles;
+          mbar_wait(bar(kFullV + tc % kStages), (tc / kStages) & 1);
+          if (more) mbar_wait(bar(kFullK + (tc + 1) % kStages), ((tc + 1) / kStages) & 1);
+          tc_fence_after_sync();
+          for (int s = 0; s < u.n_sub; ++s) {
+            pv(s, tc, j == 0);
+            if (more) qk(s, tc + 1);
+          }
+          umma_commit(bar(kEmptyV + tc % kStages));
+          if (more) {
+            umma_commit(bar(kEmptyK + (tc + 1) % kStages));
+            if (j + 2 == u.n_tiles) umma_commit(bar(kQEmpty));  // last QK of the unit issued
+          }
+        }
+        tile_count += u.n_tiles;
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================================================ softmax warpgroups A (warps 4-7), B (8-11)
+    const int sub = (warp - 4) >> 2;
+    const int row = (tid - 128) & 127;              // query row of the sub-tile = TMEM lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_base + sub * 128;
+    const uint32_t o_addr = tmem_base + lane_base + 256 + sub * 128;
+    uint32_t tile_count = 0, my_tiles = 0;          // my_tiles: tiles this warpgroup processed (phases)
+    for (int k = 0; k < n_rounds; ++k) {
+      const Unit u = unit_at(k);
+      if (u.n_tiles <= 0) continue;
+      if (sub >= u.n_sub) {  // odd group size: the B warpgroup sits this unit out
+        tile_count += u.n_tiles;
+        continue;
+      }
+      const int q_row = u.q_start + row;            // row within the request's new tokens
+      const int limit = u.cached + q_row;           // last visible key position
+      float m_used = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < u.n_tiles; ++j, ++my_tiles) {
+        const uint32_t tc = tile_count + j;
+        const int tile_begin = j * kBN;
+        mbar_wait(bar(kSFull + sub), my_tiles & 1);
+        tc_fence_after_sync();
+        const bool need_mask = (tile_begin + kBN - 1 > u.cached + u.q_start) || (tile_begin + kBN > u.kv_len);
+        // ---- pass 1: row max
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t s[32];
+          tmem_ld_x32(s_addr + c * 32, s);
+          tmem_wait_ld();
+          if (need_mask) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int key = tile_begin + c * 32 + e;
+              if (key <= limit && key < u.kv_len) mx = fmaxf(mx, __uint_as_float(s[e]));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(s[e]));
+          }
+        }
+        mx *= p.scale_log2;
+        // ---- the previous PV of this sub-tile has completed (in-order tensor pipe); observe it so
+        // that the phase of kOFull never runs ahead of us, then rescale O if the max moved a lot
+        if (j > 0) {
+          mbar_wait(bar(kOFull + sub), (my_tiles - 1) & 1);
+          tc_fence_after_sync();
+        }
+        const bool grow = mx > m_used + kRescaleThreshold;   // also true for the first tile (-inf)
+        const float m_new = grow ? mx : m_used;
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? fast_exp2(m_used - m_new) : 1.f;
+          l_run *= alpha;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld_x32(o_addr + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st_x32(o_addr + c * 32, o);
+          }
+          tmem_wait_st();
+        }
+        m_used = m_new;
+        const float m_sub = (m_used == -INFINITY) ? 0.f : m_used;
+        // ---- zero the V rows past the end of the request (page tails hold arbitrary bits)
+        {
+          const uint32_t stage = tc % kStages;
+          mbar_wait(bar(kFullV + stage), (tc / kStages) & 1);
+          const int n_valid = u.kv_len - tile_begin;
+          if (p.box_rows > 0 && n_valid < kBN) {
+            uint8_t* vt = smem + Smem::vring + stage * kTileBytes;
+            for (int idx = row; idx < (kBN - n_valid) * 16; idx += 128) {
+              const int r2 = n_valid + (idx >> 4), c16 = idx & 15;
+              *reinterpret_cast<uint4*>(vt + (c16 >> 3) * kHalfBytes + r2 * 128 + (c16 & 7) * 16) = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async_smem();
+          }
+        }
+        // ---- pass 2: P = exp2(S*scale - m), row sum, packed bf16 back to TMEM (over the S columns)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t s[32];
+          tmem_ld_x32(s_addr + c * 32, s);
+          tmem_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = fast_exp2(__uint_as_float(s[e]) * p.scale_log2 - m_sub);
+            float p1 = fast_exp2(__uint_as_float(s[e + 1]) * p.scale_log2 - m_sub);
+            if (need_mask) {
+              const int key = tile_begin + c * 32 + e;
+              if (!(key <= limit && key < u.kv_len)) p0 = 0.f;
+              if (!(key + 1 <= limit && key + 1 < u.kv_len)) p1 = 0.f;
+            }
+            l_run += p0 + p1;
+            pk[e >> 1] = pack2<T>(p0, p1);
+          }
+          tmem_st_x16(s_addr + c * 16, pk);
+        }
+        tmem_wait_st();
+        tc_fence_before_sync();
+        mbar_arrive(bar(kPFull + sub));
+      }
+      // ---- epilogue: O / l -> out
+      mbar_wait(bar(kOFull + sub), (my_tiles - 1) & 1);
+      tc_fence_after_sync();
+      const float inv = 1.f / l_run;
+      const bool store = q_row < u.q_len;
+      T* orow = p.out + ((int64_t)(u.q_begin + q_row) * p.hq + (u.head0 + sub)) * kD;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld_x32(o_addr + c * 32, o);
+        tmem_wait_ld();
+        if (store) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            Vec8 w;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              w.w[e] = pack2<T>(__uint_as_float(o[v4 * 8 + 2 * e]) * inv, __uint_as_float(o[v4 * 8 + 2 * e + 1]) * inv);
+            *reinterpret_cast<Vec8*>(orow + c * 32 + v4 * 8) = w;
+          }
+        }
+      }
+      tc_fence_before_sync();  // O / S of this sub-tile may be overwritten by the next unit's MMAs
+      tile_count += u.n_tiles;
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <typename T>
+static int launch(const Params<T>& p, const void* q, int64_t q_rs, int64_t nnz, const void* k_cache,
+                  const void* v_cache, cudaStream_t st) {
+  const bool bf16 = std::is_same<T, __nv_bfloat16>::value;
+  CUtensorMap mq, mk, mv, bk, bv;
+  const uint64_t cols = (uint64_t)p.hkv * kD;
+  if (int rc = get_tensor_map_2d(&mq, q, nnz, (uint64_t)p.hq * kD, q_rs * 2, 64, kBM, bf16)) return rc;
+  if (int rc = get_tensor_map_2d(&mk, k_cache, p.num_slots, cols, cols * 2, 64, 1, bf16)) return rc;
+  if (int rc = get_tensor_map_2d(&mv, v_cache, p.num_slots, cols, cols * 2, 64, 1, bf16)) return rc;
+  bk = mk;
+  bv = mv;
+  if (p.box_rows > 0) {
+    if (int rc = get_tensor_map_2d(&bk, k_cache, p.num_slots, cols, cols * 2, 64, p.box_rows, bf16)) return rc;
+    if (int rc = get_tensor_map_2d(&bv, v_cache, p.num_slots, cols, cols * 2, 64, p.box_rows, bf16)) return rc;
+  }
+  const size_t smem = Smem::total + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel<T>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  attn_prefill_tc_kernel<T><<<num_sms(), kThreads, smem, st>>>(p, mq, mk, mv, bk, bv);
+  B200_POST_LAUNCH();
+  return 0;
+}
+
+}  // namespace ptc
+
+// entry used by b200_attn_prefill (attn_prefill.cu)
+int launch_prefill_tc(const void* q, int64_t q_rs, int64_t nnz, const void* k_cache, const void* v_cache,
+                      const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
+                      const int32_t* cu_q, const int32_t* prefill_plan, int bs, int hq, int hkv,
+                      int64_t num_slots, int page_size, float scale_log2, void* out, int dtype,
+                      cudaStream_t st) {
+  B200_CHECK_ARG(num_slots > 0 && num_slots < (1ll << 31), "attn_prefill: bad num_slots");
+  B200_CHECK_ARG(st_stride % 4 == 0 && ((uintptr_t)slot_table % 16) == 0,
+                 "attn_prefill: slot table rows must be 16-byte aligned");
+  B200_CHECK_ARG(prefill_plan != nullptr, "attn_prefill: prefill_plan is NULL (b200_build_prefill_plan)");
+  int box_rows = 0;
+  if (page_size >= 8) {
+    box_rows = 64;
+    while (box_rows > 8 && (page_size % box_rows) != 0) box_rows >>= 1;
+    if (page_size % box_rows != 0) box_rows = 0;
+  }
+#define RUN(T_)                                                                                    \
+  ptc::Params<T_> p{slot_table, st_stride, seq_lens, cu_q, prefill_plan, bs, hq, hkv, (int)num_slots, \
+                    box_rows, scale_log2, (T_*)out};                                               \
+  return ptc::launch<T_>(p, q, q_rs, nnz, k_cache, v_cache, st)
+  if (dtype == B200_DTYPE_BF16) {
+    RUN(__nv_bfloat16);
+  }
+  RUN(__half);
+#undef RUN
+}
+
+}  // namespace b200

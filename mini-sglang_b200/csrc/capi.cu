@@ -23,14 +23,16 @@ void set_error(const char* fmt, ...) {
 
 namespace b200 {
 std::atomic<int> g_decode_impl{1};
+std::atomic<int> g_prefill_impl{1};
 std::atomic<int> g_decode_lookahead{4};
 std::atomic<int> g_decode_fused_combine{0};  // in-kernel merge costs the softmax warps more than the extra launch
 }
 
-extern "C" int b200_abi_version(void) { return 4; }
+extern "C" int b200_abi_version(void) { return 5; }
 
 extern "C" int b200_set_option(const char* name, int value) {
   if (name != nullptr && std::strcmp(name, "decode_impl") == 0) return b200::g_decode_impl.exchange(value);
+  if (name != nullptr && std::strcmp(name, "prefill_impl") == 0) return b200::g_prefill_impl.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_lookahead") == 0) return b200::g_decode_lookahead.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_fused_combine") == 0) return b200::g_decode_fused_combine.exchange(value);
   return -1;

@@ -165,9 +165,67 @@ __global__ void __launch_bounds__(1024) meta_scan_kernel(const int32_t* __restri
   }
 }
 
+// ---- prefill plan: (request, 128-row q tile) items, heaviest (most KV tiles under the causal mask)
+// first; the prefill kernel deals them to its persistent CTAs in snake order.
+// plan = {n_items, 0, 0, 0, item[...]},  item = r | q_tile << 16
+constexpr int kPrefillBins = 1024;
+__global__ void __launch_bounds__(1024) meta_prefill_plan_kernel(const int32_t* __restrict__ req_info,
+                                                                 int bs, int32_t* __restrict__ plan,
+                                                                 int capacity) {
+  __shared__ int hist[kPrefillBins];
+  __shared__ int s_total;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kPrefillBins; i += 1024) hist[i] = 0;
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  auto work_of = [&](int cached, int kl, int qt) {
+    const int ql = kl - cached;
+    const int kv_hi = min(kl, cached + min(ql, (qt + 1) * 128));
+    const int t = (kv_hi + 127) / 128;
+    return t < kPrefillBins - 1 ? t : kPrefillBins - 1;
+  };
+  for (int r = tid; r < bs; r += 1024) {
+    const int cached = req_info[3 * r + 1], kl = req_info[3 * r + 2];
+    const int nq = (kl - cached + 127) / 128;
+    for (int qt = 0; qt < nq; ++qt) atomicAdd(&hist[work_of(cached, kl, qt)], 1);
+    atomicAdd(&s_total, nq);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int b = kPrefillBins - 1; b >= 0; --b) {
+      const int n = hist[b];
+      hist[b] = run;
+      run += n;
+    }
+    plan[0] = s_total <= capacity ? s_total : -1;  // -1: the caller's buffer is too small
+    plan[1] = plan[2] = plan[3] = 0;
+  }
+  __syncthreads();
+  if (s_total > capacity) return;
+  for (int r = tid; r < bs; r += 1024) {
+    const int cached = req_info[3 * r + 1], kl = req_info[3 * r + 2];
+    const int nq = (kl - cached + 127) / 128;
+    for (int qt = 0; qt < nq; ++qt) {
+      const int pos = atomicAdd(&hist[work_of(cached, kl, qt)], 1);
+      plan[4 + pos] = r | (qt << 16);
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_build_prefill_plan(const int32_t* req_info, int bs, int32_t* prefill_plan,
+                                       int capacity_items, void* stream) {
+  B200_CHECK_ARG(bs > 0 && bs < 65536, "build_prefill_plan: batch size %d out of range", bs);
+  B200_CHECK_ARG(capacity_items > 0 && prefill_plan != nullptr, "build_prefill_plan: no buffer");
+  meta_prefill_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(req_info, bs, prefill_plan,
+                                                                  capacity_items);
+  B200_POST_LAUNCH();
+  return 0;
+}
 
 extern "C" size_t b200_decode_plan_ints(int bs) {
   return (size_t)kPlanHeader + (size_t)bs + 1 + (size_t)kMaxSplits * bs;

@@ -136,6 +136,13 @@ def test_decode_second_layer_of_pool(b200, native_lib, decode_impl):
     _run_case(b200, page_size=16, hq=16, hkv=8, lens=DECODE_LENS["tiny"], phase="decode", layer=2, layers=3)
 
 
+@pytest.fixture(params=[1, 0], ids=["tcgen05", "mmasync"])
+def prefill_impl(request, b200, native_lib):
+    prev = b200._cabi.set_option("prefill_impl", request.param)
+    yield request.param
+    b200._cabi.set_option("prefill_impl", prev)
+
+
 PREFILL_LENS = {
     "no_cache": [(0, 1), (0, 17), (0, 64), (0, 65), (0, 200), (0, 333)],
     "single_long": [(0, 1024)],
@@ -146,7 +153,7 @@ PREFILL_LENS = {
 
 @pytest.mark.parametrize("page_size", [1, 16, 64])
 @pytest.mark.parametrize("name", list(PREFILL_LENS))
-def test_prefill_qwen3_0p6b_shape(b200, native_lib, page_size, name):
+def test_prefill_qwen3_0p6b_shape(b200, native_lib, page_size, name, prefill_impl):
     lens = PREFILL_LENS[name]
     if page_size > 1 and name in ("extend", "chunked"):
         lens = [((c // page_size) * page_size, d) for c, d in lens]  # cached prefixes are page aligned
@@ -154,12 +161,12 @@ def test_prefill_qwen3_0p6b_shape(b200, native_lib, page_size, name):
     _run_case(b200, page_size=page_size, hq=16, hkv=8, lens=lens, phase="prefill")
 
 
-@pytest.mark.parametrize("hq,hkv", [(40, 8), (8, 1), (64, 8), (4, 4)])
-def test_prefill_gqa_groups(b200, native_lib, hq, hkv):
+@pytest.mark.parametrize("hq,hkv", [(40, 8), (8, 1), (64, 8), (4, 4), (6, 2)])
+def test_prefill_gqa_groups(b200, native_lib, hq, hkv, prefill_impl):
     _run_case(b200, page_size=16, hq=hq, hkv=hkv, lens=[(0, 130), (64, 300), (0, 7)], phase="prefill")
 
 
-def test_prefill_radix_shared_prefix_pages(b200, native_lib):
+def test_prefill_radix_shared_prefix_pages(b200, native_lib, prefill_impl):
     """Two requests whose leading page-table entries are identical (radix-shared pages)."""
     rel = _run_case(b200, page_size=16, hq=16, hkv=8, lens=[(0, 300), (128, 260), (128, 400)],
                     phase="prefill", share_prefix=0)
