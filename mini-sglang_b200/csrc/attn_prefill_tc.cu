@@ -14,11 +14,13 @@
 //                 S_s = Q_s . K^T            (A, B from smem, K-major, 128B swizzle)  128x128 fp32
 //                 O_s += P_s . V             (A = P_s from TMEM, B = V tile MN-major)  128x128 fp32
 //               issue order per KV tile j:  PV_A(j) QK_A(j+1) PV_B(j) QK_B(j+1)  (in-order tensor pipe)
-//   warps 4-7   softmax warpgroup A, warps 8-11 softmax warpgroup B: thread i owns query row i
-//               (TMEM lane i): row max / exp2 / row sum with no cross-thread traffic, P written back
-//               to TMEM as packed bf16 over the S columns, O rescaled in TMEM only when the running
-//               max moved by more than 2^8 (lazy correction), final O/l -> bf16 -> global.
-// TMEM: S_A 0..127 (P_A aliases 0..63), S_B 128..255, O_A 256..383, O_B 384..511.
+//   warps 4-19  softmax, 8 warps per sub-tile: two threads per query row (TMEM lane), one per half of
+//               the 128 score columns; they exchange only the tile's row max (smem + named barrier).
+//               exp2 / row sum per thread, P written back to TMEM as packed bf16 over the thread's own
+//               S columns, O rescaled in TMEM only when the running max moved by more than 2^8 (lazy
+//               correction), chunks of 32 columns that are fully masked for the whole warp are skipped,
+//               final O/l -> bf16 -> global.
+// TMEM: S_A 0..127 (P_A aliases 0..31 and 64..95), S_B 128..255, O_A 256..383, O_B 384..511.
 // The KV append of the new rows is done by the store kernel issued in front by the same C call.
 #include "b200attn.h"
 #include "common.cuh"
@@ -39,7 +41,7 @@ constexpr int kD = 128;
 constexpr int kBM = 128;                   // query rows per sub-tile
 constexpr int kBN = 128;                   // keys per tile
 constexpr int kStages = 2;                 // K ring depth = V ring depth
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;              // 4 control warps + 16 softmax warps
 constexpr int kHalfBytes = 128 * 128;      // [128 rows x 64 cols] bf16, 128B-swizzled: 16 KB
 constexpr int kTileBytes = 2 * kHalfBytes; // 32 KB
 constexpr int kMaxUnitsSmem = 64;
@@ -52,7 +54,8 @@ struct Smem {
   static constexpr int vring = kring + kStages * kTileBytes;
   static constexpr int bars = vring + kStages * kTileBytes;  // 16 mbarriers
   static constexpr int tmem_ptr = bars + 16 * 8;
-  static constexpr int units = tmem_ptr + 16;
+  static constexpr int red = tmem_ptr + 16;                 // [3][2 sub][2 half][128] floats
+  static constexpr int units = red + 3 * 2 * 2 * 128 * 4;
   static constexpr int total = units + kMaxUnitsSmem * 48;
 };
 enum Bar { kFullK = 0, kEmptyK = 2, kFullV = 4, kEmptyV = 6, kQFull = 8, kQEmpty = 9, kSFull = 10, kPFull = 12, kOFull = 14 };
@@ -155,7 +158,7 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
     mbar_init(bar(kQEmpty), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(kSFull + s), 1);
-      mbar_init(bar(kPFull + s), 128);
+      mbar_init(bar(kPFull + s), 256);
       mbar_init(bar(kOFull + s), 1);
     }
     fence_barrier_init();
@@ -273,7 +276,8 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
         for (int kk = 0; kk < 8; ++kk) {
           // B = V (MN-major): 16 keys = two 8-key swizzle atoms (1024 B each); dims 64..127 at +16 KB
           const uint64_t db = make_smem_desc(vb + kk * 2048, kHalfBytes, 1024, kLayoutSW128);
-          umma_f16_ts(d, pa + kk * 8, db, idesc_pv, (!first) || kk > 0);
+          // P: keys 0-63 packed in columns 0-31, keys 64-127 in columns 64-95 of the sub-tile
+          umma_f16_ts(d, pa + (kk >> 2) * 64 + (kk & 3) * 8, db, idesc_pv, (!first) || kk > 0);
         }
         umma_commit(bar(kOFull + s));
       };
@@ -308,12 +312,18 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
       }
     }
   } else if (warp >= 4) {
-    // ============================================================ softmax warpgroups A (warps 4-7), B (8-11)
-    const int sub = (warp - 4) >> 2;
-    const int row = (tid - 128) & 127;              // query row of the sub-tile = TMEM lane
+    // ============================================================ softmax: 16 warps.
+    // sub-tile A: warps 4-7 (score columns 0-63) + 12-15 (columns 64-127); B: warps 8-11 + 16-19.
+    // Two threads share a query row (same TMEM lane, different column halves) and exchange only the
+    // per-tile row max through smem; row sums stay per thread until the epilogue.
+    const int sw = warp - 4;
+    const int sub = (sw >> 2) & 1;
+    const int half = sw >> 3;
+    const int row = (warp & 3) * 32 + lane;         // query row of the sub-tile = TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_base + sub * 128;
-    const uint32_t o_addr = tmem_base + lane_base + 256 + sub * 128;
+    const uint32_t s_addr = tmem_base + lane_base + sub * 128 + half * 64;        // my 64 score columns
+    const uint32_t o_addr = tmem_base + lane_base + 256 + sub * 128 + half * 64;  // my 64 output columns
+    float* red = reinterpret_cast<float*>(smem + Smem::red);  // [2 parity][2 sub][2 half][128]
     uint32_t tile_count = 0, my_tiles = 0;          // my_tiles: tiles this warpgroup processed (phases)
     for (int k = 0; k < n_rounds; ++k) {
       const Unit u = unit_at(k);
@@ -323,33 +333,52 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
         continue;
       }
       const int q_row = u.q_start + row;            // row within the request's new tokens
-      const int limit = u.cached + q_row;           // last visible key position
+      const int vis_end = min(u.cached + q_row + 1, u.kv_len);  // keys [0, vis_end) are visible
       float m_used = -INFINITY, l_run = 0.f;
       for (int j = 0; j < u.n_tiles; ++j, ++my_tiles) {
         const uint32_t tc = tile_count + j;
         const int tile_begin = j * kBN;
         mbar_wait(bar(kSFull + sub), my_tiles & 1);
         tc_fence_after_sync();
-        const bool need_mask = (tile_begin + kBN - 1 > u.cached + u.q_start) || (tile_begin + kBN > u.kv_len);
-        // ---- pass 1: row max
-        float mx = -INFINITY;
+        // visible keys of this row inside the tile form a prefix [0, n_vis); rows of a warp are
+        // consecutive, so lane 0 / lane 31 bound the warp: whole 32-column chunks are either
+        // skipped, unmasked, or (at most two of them) masked element-wise -- warp-uniform branches
+        const int n_vis = max(0, min(kBN, vis_end - tile_begin));
+        const int n_lo = __shfl_sync(0xffffffffu, n_vis, 0), n_hi = __shfl_sync(0xffffffffu, n_vis, 31);
+        // ---- pass 1: row max over my 64 columns
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = half * 64 + c * 32;
+          if (col0 >= n_hi) continue;  // every row of this warp has the chunk masked
           uint32_t s[32];
           tmem_ld_x32(s_addr + c * 32, s);
           tmem_wait_ld();
-          if (need_mask) {
+          if (col0 + 32 <= n_lo) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int key = tile_begin + c * 32 + e;
-              if (key <= limit && key < u.kv_len) mx = fmaxf(mx, __uint_as_float(s[e]));
+            for (int e = 0; e < 32; e += 4) {
+              mx0 = fmaxf(mx0, __uint_as_float(s[e]));
+              mx1 = fmaxf(mx1, __uint_as_float(s[e + 1]));
+              mx2 = fmaxf(mx2, __uint_as_float(s[e + 2]));
+              mx3 = fmaxf(mx3, __uint_as_float(s[e + 3]));
             }
           } else {
+            const int nv = n_vis - col0;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(s[e]));
+            for (int e = 0; e < 32; e += 4) {
+              mx0 = fmaxf(mx0, e < nv ? __uint_as_float(s[e]) : -INFINITY);
+              mx1 = fmaxf(mx1, e + 1 < nv ? __uint_as_float(s[e + 1]) : -INFINITY);
+              mx2 = fmaxf(mx2, e + 2 < nv ? __uint_as_float(s[e + 2]) : -INFINITY);
+              mx3 = fmaxf(mx3, e + 3 < nv ? __uint_as_float(s[e + 3]) : -INFINITY);
+            }
           }
         }
-        mx *= p.scale_log2;
+        float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        // exchange with the thread holding the other half of the row
+        float* rp = red + ((my_tiles & 1) * 4 + sub * 2) * 128;
+        rp[half * 128 + row] = mx;
+        named_bar_sync(1 + sub, 256);
+        mx = fmaxf(mx, rp[(half ^ 1) * 128 + row]) * p.scale_log2;
         // ---- the previous PV of this sub-tile has completed (in-order tensor pipe); observe it so
         // that the phase of kOFull never runs ahead of us, then rescale O if the max moved a lot
         if (j > 0) {
@@ -362,7 +391,7 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
           const float alpha = grow ? fast_exp2(m_used - m_new) : 1.f;
           l_run *= alpha;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
             tmem_ld_x32(o_addr + c * 32, o);
             tmem_wait_ld();
@@ -379,7 +408,7 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
           const uint32_t stage = tc % kStages;
           mbar_wait(bar(kFullV + stage), (tc / kStages) & 1);
           const int n_valid = u.kv_len - tile_begin;
-          if (p.box_rows > 0 && n_valid < kBN) {
+          if (p.box_rows > 0 && n_valid < kBN && half == 0) {
             uint8_t* vt = smem + Smem::vring + stage * kTileBytes;
             for (int idx = row; idx < (kBN - n_valid) * 16; idx += 128) {
               const int r2 = n_valid + (idx >> 4), c16 = idx & 15;
@@ -388,39 +417,59 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
             fence_proxy_async_smem();
           }
         }
-        // ---- pass 2: P = exp2(S*scale - m), row sum, packed bf16 back to TMEM (over the S columns)
+        // ---- pass 2: P = exp2(S*scale - m), row sum, packed bf16 back to TMEM over my own S
+        // columns (keys 0-63 -> columns 0-31, keys 64-127 -> columns 64-95 of the sub-tile)
+        float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t s[32];
-          tmem_ld_x32(s_addr + c * 32, s);
-          tmem_wait_ld();
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = half * 64 + c * 32;
           uint32_t pk[16];
+          if (col0 >= n_hi) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float p0 = fast_exp2(__uint_as_float(s[e]) * p.scale_log2 - m_sub);
-            float p1 = fast_exp2(__uint_as_float(s[e + 1]) * p.scale_log2 - m_sub);
-            if (need_mask) {
-              const int key = tile_begin + c * 32 + e;
-              if (!(key <= limit && key < u.kv_len)) p0 = 0.f;
-              if (!(key + 1 <= limit && key + 1 < u.kv_len)) p1 = 0.f;
+            for (int e = 0; e < 16; ++e) pk[e] = 0u;
+          } else {
+            uint32_t s[32];
+            tmem_ld_x32(s_addr + c * 32, s);
+            tmem_wait_ld();
+            if (col0 + 32 <= n_lo) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 2) {
+                const float p0 = fast_exp2(fmaf(__uint_as_float(s[e]), p.scale_log2, -m_sub));
+                const float p1 = fast_exp2(fmaf(__uint_as_float(s[e + 1]), p.scale_log2, -m_sub));
+                l0 += p0;
+                l1 += p1;
+                pk[e >> 1] = pack2<T>(p0, p1);
+              }
+            } else {
+              const int nv = n_vis - col0;
+#pragma unroll
+              for (int e = 0; e < 32; e += 2) {
+                const float p0 = e < nv ? fast_exp2(fmaf(__uint_as_float(s[e]), p.scale_log2, -m_sub)) : 0.f;
+                const float p1 = e + 1 < nv ? fast_exp2(fmaf(__uint_as_float(s[e + 1]), p.scale_log2, -m_sub)) : 0.f;
+                l0 += p0;
+                l1 += p1;
+                pk[e >> 1] = pack2<T>(p0, p1);
+              }
             }
-            l_run += p0 + p1;
-            pk[e >> 1] = pack2<T>(p0, p1);
           }
           tmem_st_x16(s_addr + c * 16, pk);
         }
+        l_run += l0 + l1;
         tmem_wait_st();
         tc_fence_before_sync();
         mbar_arrive(bar(kPFull + sub));
       }
-      // ---- epilogue: O / l -> out
+      // ---- epilogue: O / l -> out (my 64 output columns); l = sum of the two half-row sums
+      float* lp = red + (2 * 4 + sub * 2) * 128;  // third buffer, after the two parity buffers
+      lp[half * 128 + row] = l_run;
       mbar_wait(bar(kOFull + sub), (my_tiles - 1) & 1);
       tc_fence_after_sync();
-      const float inv = 1.f / l_run;
+      named_bar_sync(1 + sub, 256);
+      const float inv = 1.f / (l_run + lp[(half ^ 1) * 128 + row]);
       const bool store = q_row < u.q_len;
-      T* orow = p.out + ((int64_t)(u.q_begin + q_row) * p.hq + (u.head0 + sub)) * kD;
+      T* orow = p.out + ((int64_t)(u.q_begin + q_row) * p.hq + (u.head0 + sub)) * kD + half * 64;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t o[32];
         tmem_ld_x32(o_addr + c * 32, o);
         tmem_wait_ld();
@@ -436,6 +485,7 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
         }
       }
       tc_fence_before_sync();  // O / S of this sub-tile may be overwritten by the next unit's MMAs
+      named_bar_sync(1 + sub, 256);  // lp is reused by the next unit
       tile_count += u.n_tiles;
     }
   }
