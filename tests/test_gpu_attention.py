@@ -294,3 +294,43 @@ def test_decode_full_size_properties(b200, native_lib, decode_impl):
     out3 = gw.backend.forward(qg.view(-1, hq, d), kg, vg * 2, 0, batch)
     torch.cuda.synchronize()
     assert (out3.float() - 2 * out2.float()).abs().max().item() <= 2e-2 * out3.float().abs().max().item()
+
+
+@pytest.mark.parametrize("phase", ["decode", "prefill"])
+def test_attention_against_flashinfer_golden(b200, native_lib, phase):
+    """Product path vs the outputs FlashInfer (fa2 wrappers, the reference's parity oracle) produced
+    for the same inputs on a B200 (tests/golden/make_flashinfer_golden.py)."""
+    from pathlib import Path
+
+    from helpers import World
+
+    fi = np.load(Path(__file__).parent / "golden" / "flashinfer_golden.npz")
+    bf = lambda a: torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)  # noqa: E731
+    hq, hkv, d, ps = 4, 2, 128, 16
+    reqs = [tuple(r) for r in fi[f"{phase}_reqs"].tolist()]
+    pt = fi[f"{phase}_page_table"]
+    used = fi[f"{phase}_used_slots"]
+    num_pages = (int(pt.max()) // ps) + 1
+    pool = torch.zeros((2, 1, (num_pages + 1) * ps, hkv, d), dtype=torch.bfloat16)
+    pool[0, 0, torch.from_numpy(used).long()] = bf(fi[f"{phase}_k_rows"])
+    pool[1, 0, torch.from_numpy(used).long()] = bf(fi[f"{phase}_v_rows"])
+    w = World(ps, num_pages, hq, hkv, d, 1, torch.bfloat16, pt.copy(), [], pool, reqs)
+    md = o_meta.ref_prepare_metadata(pt, reqs, ps)
+    gw = GpuWorld(b200, w)
+    batch = gw.batch(phase)
+    loc = torch.from_numpy(md.out_loc.astype(np.int64))
+    q = bf(fi[f"{phase}_q"]).cuda()
+    k_new = pool[0, 0, loc].reshape(len(loc), -1).cuda()  # the golden pool already holds the appended rows
+    v_new = pool[1, 0, loc].reshape(len(loc), -1).cuda()
+    batch.out_loc = torch.from_numpy(md.out_loc).cuda()
+    batch.positions = torch.from_numpy(md.positions).cuda()
+    gw.backend.prepare_metadata(batch)
+    out = gw.backend.forward(q, k_new, v_new, 0, batch)
+    torch.cuda.synchronize()
+    want = bf(fi[f"{phase}_out"]).float()
+    got = out.float().cpu()
+    scale = want.abs().max().item()
+    # both sides are bf16 outputs of bf16-P tensor-core pipelines: 1e-3 relative + one output ulp each
+    bound = 1e-3 * scale + 2.0**-7 * want.abs() + 1e-6
+    assert ((got - want).abs() <= bound).all(), ((got - want).abs() - bound).max()
+    assert ((got - want).norm() / want.norm()).item() < 2.5e-3

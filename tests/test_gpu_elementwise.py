@@ -151,3 +151,40 @@ def test_fused_qknorm_rope_equals_three_launches(b200, native_lib, with_norm):
     b200.ops.apply_rope_with_cos_sin_cache_inplace(pos, qa, ka, d, cache)
     b200.ops.qknorm_rope_inplace(pos, b[:, : hq * d], b[:, hq * d : (hq + hkv) * d], d, cache, qw, kw, 1e-6)
     assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+
+# ------------------------------------------------------------------ against FlashInfer itself
+def _fi():
+    import numpy as np
+    from pathlib import Path
+
+    return np.load(Path(__file__).parent / "golden" / "flashinfer_golden.npz")
+
+
+def _bf(a):
+    import numpy as np
+
+    return torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16).cuda()
+
+
+def test_rope_and_norms_bit_identical_to_flashinfer(b200, native_lib):
+    """Golden outputs of the FlashInfer ops the reference binds (layers/rotary.py:45, norm.py:16-38):
+    the B200 kernels reproduce them bit for bit."""
+    fi = _fi()
+    hq, hkv, d = 4, 2, 128
+    x = _bf(fi["rope_x"])
+    pos = torch.from_numpy(fi["rope_pos"]).cuda()
+    from oracle.rope import ref_cos_sin_cache
+
+    b200.ops.apply_rope_with_cos_sin_cache_inplace(pos, x[:, : hq * d], x[:, hq * d : (hq + hkv) * d], d,
+                                                   ref_cos_sin_cache(d, 1024, 1e6).cuda())
+    assert torch.equal(x.view(torch.int16), _bf(fi["rope_out"]).view(torch.int16))
+    y = b200.ops.rmsnorm(_bf(fi["norm_x"]), _bf(fi["norm_w"]), 1e-6)
+    assert torch.equal(y.view(torch.int16), _bf(fi["norm_out"]).view(torch.int16))
+    xh = _bf(fi["qknorm_x"])
+    b200.ops.rmsnorm(xh, _bf(fi["qknorm_w"]), 1e-6, out=xh)
+    assert torch.equal(xh.view(torch.int16), _bf(fi["qknorm_out"]).view(torch.int16))
+    xf, rf = _bf(fi["fused_x"]), _bf(fi["fused_res"])
+    b200.ops.fused_add_rmsnorm(xf, rf, _bf(fi["norm_w"]), 1e-6)
+    assert torch.equal(xf.view(torch.int16), _bf(fi["fused_x_out"]).view(torch.int16))
+    assert torch.equal(rf.view(torch.int16), _bf(fi["fused_res_out"]).view(torch.int16))

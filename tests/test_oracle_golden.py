@@ -107,3 +107,59 @@ def test_norm_oracle_properties():
     nx, nr = o_norm.ref_fused_add_rmsnorm(x, x, w, 1e-6)
     assert torch.equal(nr, (x.float() * 2).to(torch.bfloat16))
     assert torch.allclose(nx.float(), o_norm.ref_rmsnorm((x.float() * 2), w.float(), 1e-6), atol=2e-2)
+
+
+# ------------------------------------------------------------------ floating-point side
+# tests/golden/flashinfer_golden.npz: inputs + outputs of FlashInfer 0.6.11.post2 called exactly as
+# the reference's call sites do, produced on a B200 by tests/golden/make_flashinfer_golden.py.
+FI = np.load(Path(__file__).parent / "golden" / "flashinfer_golden.npz")
+
+
+def _bf16(a: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)
+
+
+@pytest.mark.parametrize("phase", ["decode", "prefill"])
+def test_attention_oracle_matches_flashinfer(phase):
+    reqs = [tuple(r) for r in FI[f"{phase}_reqs"].tolist()]
+    pt = FI[f"{phase}_page_table"]
+    q = _bf16(FI[f"{phase}_q"])
+    used = FI[f"{phase}_used_slots"]
+    k_rows, v_rows = _bf16(FI[f"{phase}_k_rows"]), _bf16(FI[f"{phase}_v_rows"])
+    remap = {int(s): i for i, s in enumerate(used)}
+    want = _bf16(FI[f"{phase}_out"]).float()
+    off = 0
+    for (t, c, d) in reqs:
+        rows = torch.tensor([remap[int(s)] for s in pt[t, :d]])
+        ql = d - c
+        got = o_attn.ref_attention_one(q[off : off + ql], k_rows[rows], v_rows[rows], 128**-0.5)
+        ref = want[off : off + ql]
+        scale = ref.abs().max().item()
+        # FlashInfer output is bf16 (half an ulp <= 2^-8 |x|) and rounds P to bf16 before PV
+        bound = 2e-3 * scale + 2.0**-8 * ref.abs() + 1e-6
+        assert ((got - ref).abs() <= bound).all(), ((got - ref).abs() - bound).max()
+        off += ql
+
+
+def test_rope_oracle_matches_flashinfer():
+    x, pos = _bf16(FI["rope_x"]), torch.from_numpy(FI["rope_pos"])
+    cache = o_rope.ref_cos_sin_cache(128, 1024, 1e6)
+    hq, hkv, d = 4, 2, 128
+    got = x.clone()
+    got[:, : hq * d] = o_rope.ref_apply_rope_neox(pos, x[:, : hq * d], d, cache)
+    got[:, hq * d : (hq + hkv) * d] = o_rope.ref_apply_rope_neox(pos, x[:, hq * d : (hq + hkv) * d], d, cache)
+    want = _bf16(FI["rope_out"])
+    diff = (got.float() - want.float()).abs()
+    assert (diff <= 2.0**-7 * want.float().abs() + 1e-6).all()  # <= 1 bf16 ulp (FMA contraction)
+    assert (got.view(torch.int16) == want.view(torch.int16)).float().mean() > 0.99
+
+
+def test_norm_oracle_matches_flashinfer():
+    for xk, wk, ok in (("norm_x", "norm_w", "norm_out"), ("qknorm_x", "qknorm_w", "qknorm_out")):
+        got = o_norm.ref_rmsnorm(_bf16(FI[xk]), _bf16(FI[wk]), 1e-6)
+        want = _bf16(FI[ok])
+        assert ((got.float() - want.float()).abs() <= 2.0**-7 * want.float().abs() + 1e-6).all()
+    gx, gr = o_norm.ref_fused_add_rmsnorm(_bf16(FI["fused_x"]), _bf16(FI["fused_res"]), _bf16(FI["norm_w"]), 1e-6)
+    assert torch.equal(gr.view(torch.int16), _bf16(FI["fused_res_out"]).view(torch.int16))  # residual: exact
+    wx = _bf16(FI["fused_x_out"])
+    assert ((gx.float() - wx.float()).abs() <= 2.0**-7 * wx.float().abs() + 1e-6).all()
