@@ -48,7 +48,7 @@ constexpr int kD = 128;
 constexpr int kTileN = 128;                 // keys per tile
 constexpr int kStages = 3;
 constexpr int kThreads = 384;
-constexpr int kWarpMma = 8, kWarpQ = 9;
+constexpr int kWarpMma = 8, kWarpQ = 9, kWarpCombine = 10;
 constexpr int kHalfBytes = kTileN * 128;    // one 64-column half of a K or V tile: 16 KB
 constexpr int kStageBytes = 2 * kHalfBytes; // one K (or V) tile: half 0 | half 1 = 32 KB
 constexpr int kQBufBytes = 2 * 2048;        // two halves of [16 rows x 128 B]
@@ -64,13 +64,14 @@ struct Smem {
   static constexpr int vring = kStages * kStageBytes;      // V tiles, released after PV
   static constexpr int qbuf = 2 * kStages * kStageBytes;
   static constexpr int pbuf = qbuf + 2 * kQBufBytes;
-  static constexpr int bars = pbuf + 2 * kPBufBytes;      // 22 mbarriers
-  static constexpr int tmem_ptr = bars + 24 * 8;
+  static constexpr int bars = pbuf + 2 * kPBufBytes;      // 32 mbarriers
+  static constexpr int tmem_ptr = bars + 32 * 8;
   static constexpr int red = tmem_ptr + 16;               // [2][4][16] floats (tile max), [4][16] (sums)
   static constexpr int units = red + (2 * 4 * 16 + 4 * 16 + 4 * 16) * 4;  // decoded work units
   static constexpr int total = units + kMaxUnitsSmem * 40;
 };
-enum Bar { kFullK = 0, kEmptyK = 3, kFullV = 6, kEmptyV = 9, kSFull = 12, kPFull = 16, kOFull = 18, kQFull = 20, kQEmpty = 22 };
+enum Bar { kFullK = 0, kEmptyK = 3, kFullV = 6, kEmptyV = 9, kSFull = 12, kPFull = 16, kOFull = 18, kQFull = 20, kQEmpty = 22, kFinFull = 24, kFinEmpty = 28 };
+constexpr int kFinRing = 4;  // units in flight between the softmax warps and the combiner warp
 
 template <typename T>
 struct Params {
@@ -180,6 +181,10 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
       mbar_init(bar(kEmptyV + s), 1);
     }
     for (int b = 0; b < kNumS; ++b) mbar_init(bar(kSFull + b), 1);
+    for (int b = 0; b < kFinRing; ++b) {
+      mbar_init(bar(kFinFull + b), 128);
+      mbar_init(bar(kFinEmpty + b), 1);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(kPFull + b), 128);
       mbar_init(bar(kOFull + b), 1);
@@ -391,7 +396,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     float* red_max = red;              // [2][4][16]
     float* red_sum = red + 2 * 4 * 16; // [4][16]
     float* red_new = red_sum + 4 * 16; // [4][16]
-    uint32_t tile_count = 0;
+    uint32_t tile_count = 0, fin_count = 0;
     for (int k = 0; k < n_rounds; ++k) {
       const Unit u = unit_at(k);
       if (u.n_tiles < 0) continue;  // no unit for this CTA in the last round
@@ -542,38 +547,70 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
           p.part_ml[(base + ct) * 2 + 0] = mm;
           p.part_ml[(base + ct) * 2 + 1] = ll;
         }
-        // ---- fused split-KV combine: the unit that arrives last for (request, kv head) merges
-        // all partials (flash-decoding reduction) -- no second launch, no grid-wide wait.
-        if (!p.fused_combine) continue;
-        __threadfence();            // our partials are visible device-wide before we count in
-        named_bar_sync(1, 128);
-        int* flag = reinterpret_cast<int*>(red_new);
-        if (ct == 0) {
-          const int old = atomicAdd(p.counters + u.r * p.hkv + u.h, 1);
-          *flag = (old == u.n_chunks - 1);
-          if (old == u.n_chunks - 1) p.counters[u.r * p.hkv + u.h] = 0;  // leave it zero for the next launch
+        // ---- hand the unit to the combiner warp (asynchronous split-KV merge): the softmax warps
+        // only pay an mbarrier arrive; the release/acquire pair orders the partial stores above
+        // before the combiner's device-scope fence + arrival counter.
+        if (p.fused_combine) {
+          const uint32_t slot = fin_count % kFinRing;
+          mbar_wait(bar(kFinEmpty + slot), ((fin_count / kFinRing) & 1) ^ 1);
+          mbar_arrive(bar(kFinFull + slot));
+          ++fin_count;
         }
-        named_bar_sync(1, 128);
-        const bool is_last = *flag != 0;
-        named_bar_sync(1, 128);     // flag (aliases red_new) is reused by the next unit
-        if (is_last) {
-          __threadfence();          // acquire: the other chunks' partials
+      }
+    }
+  } else if (warp == kWarpCombine) {
+    // ============================================================ split-KV combiner (one warp)
+    // For every multi-chunk unit of this CTA: count in on the (request, kv head) arrival counter;
+    // whoever arrives last merges all partials (flash-decoding reduction) and writes the output.
+    if (p.fused_combine) {
+      uint32_t fin_count = 0;
+      for (int k = 0; k < n_rounds; ++k) {
+        const Unit u = unit_at(k);
+        if (u.n_tiles < 0 || u.n_chunks == 1) continue;
+        const uint32_t slot = fin_count % kFinRing;
+        mbar_wait(bar(kFinFull + slot), (fin_count / kFinRing) & 1);
+        ++fin_count;
+        __threadfence();
+        int last = 0;
+        if (lane == 0) {
+          const int old = atomicAdd(p.counters + u.r * p.hkv + u.h, 1);
+          last = (old == u.n_chunks - 1);
+          if (last) p.counters[u.r * p.hkv + u.h] = 0;  // zero again for the next launch
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          __threadfence();  // acquire the other chunks' partials
           const int64_t b0 = ((int64_t)u.r * kMaxSplits) * p.hq + u.h * G;
-#pragma unroll
           for (int g = 0; g < G; ++g) {
-            float mx = -INFINITY;
-            for (int c = 0; c < u.n_chunks; ++c)
-              mx = fmaxf(mx, __ldcg(p.part_ml + (b0 + (int64_t)c * p.hq + g) * 2));
-            float o = 0.f, l = 0.f;
-            for (int c = 0; c < u.n_chunks; ++c) {
-              const int64_t idx = b0 + (int64_t)c * p.hq + g;
-              const float w = fast_exp2(__ldcg(p.part_ml + idx * 2) - mx);
-              l += w * __ldcg(p.part_ml + idx * 2 + 1);
-              o += w * __ldcg(p.part_o + idx * kD + ct);
+            // lane c holds (m, l) of chunk c
+            float mc = -INFINITY, lc = 0.f;
+            if (lane < u.n_chunks) {
+              const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml + (b0 + (int64_t)lane * p.hq + g) * 2));
+              mc = ml.x;
+              lc = ml.y;
             }
-            p.out[((int64_t)u.r * p.hq + u.h * G + g) * kD + ct] = DTypeTraits<T>::from_float(o / l);
+            const float mx = warp_max(mc);
+            const float wc = lane < u.n_chunks ? fast_exp2(mc - mx) : 0.f;
+            const float inv = 1.f / warp_sum(wc * lc);
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = 0; c < u.n_chunks; ++c) {
+              const float w = __shfl_sync(0xffffffffu, wc, c);
+              const float4 po = __ldcg(reinterpret_cast<const float4*>(p.part_o + (b0 + (int64_t)c * p.hq + g) * kD) + lane);
+              o.x += w * po.x;
+              o.y += w * po.y;
+              o.z += w * po.z;
+              o.w += w * po.w;
+            }
+            typename DTypeTraits<T>::T2 lo = DTypeTraits<T>::from_float2(o.x * inv, o.y * inv);
+            typename DTypeTraits<T>::T2 hi = DTypeTraits<T>::from_float2(o.z * inv, o.w * inv);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(p.out + ((int64_t)u.r * p.hq + u.h * G + g) * kD + lane * 4) = pk;
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kFinEmpty + slot));
       }
     }
   }
