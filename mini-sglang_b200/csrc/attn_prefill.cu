@@ -322,8 +322,8 @@ static int launch_prefill(const PrefillParams<T>& p, int max_q, cudaStream_t st)
 
 namespace b200 {
 extern std::atomic<int> g_prefill_impl;
-int launch_prefill_tc(const void* q, int64_t q_rs, int64_t nnz, const void* k_cache, const void* v_cache,
-                      const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
+int launch_prefill_tc(const void* q, int64_t q_rs, int64_t nnz, const void* k, const void* v, int64_t kv_rs,
+                      void* k_cache, void* v_cache, const int32_t* out_loc, const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
                       const int32_t* cu_q, const int32_t* prefill_plan, int bs, int hq, int hkv,
                       int64_t num_slots, int page_size, float scale_log2, void* out, int dtype,
                       cudaStream_t st);
@@ -356,17 +356,17 @@ extern "C" int b200_attn_prefill(const void* q, int64_t q_row_stride, const void
                  "attn_prefill: pointers must be 16-byte aligned");
   B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "attn_prefill: bad dtype %d",
                  dtype);
+  auto st = (cudaStream_t)stream;
+  const float scale_log2 = scale * kLog2e;
+  if (prefill_plan != nullptr && g_prefill_impl.load() == 1 && (hq / hkv) <= 16)  // append fused
+    return launch_prefill_tc(q, q_row_stride, nnz, k, v, k_row_stride, k_cache, v_cache, out_loc, slot_table, slot_table_stride,
+                             seq_lens, cu_seqlens_q, prefill_plan, bs, hq, hkv, num_slots, page_size,
+                             scale_log2, out, dtype, st);
   // append the new rows first (same stream => ordered before the attention kernel reads them)
   const int64_t row_bytes = (int64_t)hkv * kD * 2;
   if (int rc = b200_store_kv(k_cache, v_cache, row_bytes, k, v, k_row_stride * 2, out_loc, 0, nnz,
                              row_bytes, stream))
     return rc;
-  auto st = (cudaStream_t)stream;
-  const float scale_log2 = scale * kLog2e;
-  if (prefill_plan != nullptr && g_prefill_impl.load() == 1 && (hq / hkv) <= 16)
-    return launch_prefill_tc(q, q_row_stride, nnz, k_cache, v_cache, slot_table, slot_table_stride,
-                             seq_lens, cu_seqlens_q, prefill_plan, bs, hq, hkv, num_slots, page_size,
-                             scale_log2, out, dtype, st);
   if (dtype == B200_DTYPE_BF16) {
     PrefillParams<__nv_bfloat16> p{(const __nv_bfloat16*)q, q_row_stride,
                                    (const __nv_bfloat16*)k_cache, (const __nv_bfloat16*)v_cache,

@@ -3,13 +3,16 @@
 // python/minisgl/attention/fi.py:150-165,188; causal, bottom-right aligned).
 //
 // Compute-bound: exact causal flops = 4*Hq*D*sum_r[q*cached + q(q+1)/2].
-// Persistent, one CTA per SM, 384 threads.  A work unit is (request, 128-row query tile, kv head,
+// Persistent, one CTA per SM, 640 threads.  A work unit is (request, 128-row query tile, kv head,
 // pair of query heads of that kv head's GQA group): the two heads ("sub-tiles" A and B) share every
 // K/V tile, so K/V bytes per flop are halved and two softmax warpgroups ping-pong against one
 // tensor pipe (FlashAttention-4 style):
 //
 //   warp 0      K producer (+ the unit's Q sub-tiles): TMA boxes per page piece / gather4 rows
 //   warp 1      V producer
+//   (append)    fused KV append: before their first score tile arrives the softmax warps copy
+//               pool[out_loc[t]] = k[t], v[t]; the attention reads this forward's tokens from the
+//               k / v inputs, never back from the pool, so no ordering is needed
 //   warp 2      UMMA issuer (one thread) + TMEM allocation
 //                 S_s = Q_s . K^T            (A, B from smem, K-major, 128B swizzle)  128x128 fp32
 //                 O_s += P_s . V             (A = P_s from TMEM, B = V tile MN-major)  128x128 fp32
@@ -21,7 +24,6 @@
 //               correction), chunks of 32 columns that are fully masked for the whole warp are skipped,
 //               final O/l -> bf16 -> global.
 // TMEM: S_A 0..127 (P_A aliases 0..31 and 64..95), S_B 128..255, O_A 256..383, O_B 384..511.
-// The KV append of the new rows is done by the store kernel issued in front by the same C call.
 #include "b200attn.h"
 #include "common.cuh"
 #include "sm100.cuh"
@@ -52,8 +54,8 @@ struct Smem {
   static constexpr int q = 0;                              // 2 sub-tiles x 32 KB
   static constexpr int kring = 2 * kTileBytes;             // kStages x 32 KB
   static constexpr int vring = kring + kStages * kTileBytes;
-  static constexpr int bars = vring + kStages * kTileBytes;  // 16 mbarriers
-  static constexpr int tmem_ptr = bars + 16 * 8;
+  static constexpr int bars = vring + kStages * kTileBytes;  // 24 mbarriers
+  static constexpr int tmem_ptr = bars + 24 * 8;
   static constexpr int red = tmem_ptr + 16;                 // [3][2 sub][2 half][128] floats
   static constexpr int units = red + 3 * 2 * 2 * 128 * 4;
   static constexpr int total = units + kMaxUnitsSmem * 48;
@@ -72,6 +74,15 @@ struct Params {
   int box_rows;
   float scale_log2;
   T* out;
+  // fused KV append (rows of the new tokens -> pool); attention never reads them back from the pool
+  const T* k_new;
+  const T* v_new;
+  int64_t kv_rs;      // row stride of k_new / v_new (elements)
+  T* k_cache;
+  T* v_cache;
+  const int32_t* out_loc;
+  int64_t nnz;
+  int skip_append;  // debug: measure the attention without the fused append
 };
 
 struct Unit {
@@ -114,7 +125,11 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
                        const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_v,
                        const __grid_constant__ CUtensorMap box_k,
-                       const __grid_constant__ CUtensorMap box_v) {
+                       const __grid_constant__ CUtensorMap box_v,
+                       const __grid_constant__ CUtensorMap new_k,    // k input rows, box {64, 1}
+                       const __grid_constant__ CUtensorMap new_v,
+                       const __grid_constant__ CUtensorMap newbox_k, // k input rows, box {64, box_rows}
+                       const __grid_constant__ CUtensorMap newbox_v) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -167,6 +182,10 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
     prefetch_tensormap(&map_v);
     prefetch_tensormap(&box_k);
     prefetch_tensormap(&box_v);
+    prefetch_tensormap(&new_k);
+    prefetch_tensormap(&new_v);
+    prefetch_tensormap(&newbox_k);
+    prefetch_tensormap(&newbox_v);
   }
   if (warp == 2) tmem_alloc(sbase + Smem::tmem_ptr, kTmemCols);
   tc_fence_before_sync();
@@ -183,11 +202,72 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
     const int full0 = kind == 0 ? kFullK : kFullV, empty0 = kind == 0 ? kEmptyK : kEmptyV;
     const uint32_t ring = sbase + (kind == 0 ? Smem::kring : Smem::vring);
     uint32_t tile_count = 0, unit_count = 0;
+    // ---- fused KV append: the tile of a unit that holds the unit's own new tokens is written to the
+    // pool straight from shared memory (TMA store) when its ring slot is recycled -- no extra loads,
+    // no extra launch.  Ownership: positions [cached + q_start, cached + min(q_len, q_start + 128)) of
+    // kv head h belong to the unit of query tile q_start and the first head pair.
+    struct Pending {
+      int valid, lo, hi, tile_begin, col0;
+      uint32_t phase;
+      const int32_t* slots;
+    } pend[kStages];
+    for (int s = 0; s < kStages; ++s) pend[s].valid = 0;
+    const CUtensorMap* smap_box = bmap;   // pool, box_rows x 64 columns
+    const CUtensorMap* smap_row = gmap;   // pool, 1 x 64 columns (row-exact / scatter4)
+    // valid: 0 = nothing, 1 = tile issued (append once it has landed), 2 = stores issued
+    auto issue_stores = [&](int stage) {  // whole warp; the tile has landed
+      Pending& pd = pend[stage];
+      const uint32_t base = ring + stage * kTileBytes;
+      if (rb > 0) {
+        const int n_instr = (kBN / rb) * 2;
+        if (lane < n_instr) {
+          const int box = lane >> 1, half = lane & 1;
+          const int pb = pd.tile_begin + box * rb;
+          const uint32_t src = base + half * kHalfBytes + box * rb * 128;
+          const int col = pd.col0 + half * 64;
+          if (pb >= pd.lo && pb + rb <= pd.hi) {
+            tma_store_2d(smap_box, src, col, __ldg(pd.slots + pb));
+          } else {
+            for (int i = 0; i < rb; ++i)
+              if (pb + i >= pd.lo && pb + i < pd.hi) tma_store_2d(smap_row, src + i * 128, col, __ldg(pd.slots + pb + i));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int grp = (lane >> 1) + it * 16, half = lane & 1;
+          const int pos0 = pd.tile_begin + grp * 4;
+          int rr[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            rr[i] = (pos0 + i >= pd.lo && pos0 + i < pd.hi) ? __ldg(pd.slots + pos0 + i) : p.num_slots;  // out of range: skipped
+          if (pos0 + 4 > pd.lo && pos0 < pd.hi)
+            tma_scatter4(smap_row, base + half * kHalfBytes + grp * 512, pd.col0 + half * 64, rr[0], rr[1], rr[2], rr[3]);
+        }
+      }
+      bulk_commit();
+      pd.valid = 2;
+      __syncwarp();
+    };
+    // opportunistic: append a tile as soon as it has landed (the tensor core may still be reading it)
+    auto try_store = [&](int stage) {
+      if (pend[stage].valid == 1 && mbar_test_wait(bar(full0 + stage), pend[stage].phase)) issue_stores(stage);
+    };
+    // before a ring slot is overwritten: its tile has landed and been consumed
+    auto flush_stage = [&](int stage) {
+      if (pend[stage].valid == 1) issue_stores(stage);
+      if (pend[stage].valid == 2) {
+        bulk_wait_read0();  // the stores have read the slot (normally long ago)
+        pend[stage].valid = 0;
+      }
+    };
     for (int k = 0; k < n_rounds; ++k) {
       const Unit u = unit_at(k);
       if (u.n_tiles <= 0) continue;
       const int32_t* slots = p.slot_table + (int64_t)u.r * p.st_stride;
       const int col0 = u.h * kD;
+      const bool owner = !p.skip_append && (u.head0 == u.h * group);
+      const int own_lo = u.cached + u.q_start, own_hi = u.cached + min(u.q_len, u.q_start + kBM);
       if (kind == 0) {
         // the unit's query sub-tiles (rows past the tensor end are zero filled, rows past the
         // request's end belong to the next request: computed, never stored)
@@ -202,6 +282,20 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
         __syncwarp();
       }
       ++unit_count;
+      // Positions < cached come from the pool through the slot table; positions >= cached are the
+      // tokens of this very forward and are read straight from the k / v inputs (row q_begin + pos -
+      // cached), so the attention never depends on the append that warp 3 performs concurrently.
+      // Rows past the end of the request are other requests' tokens or out of range (zeros): finite,
+      // and masked by position.
+      const CUtensorMap* nmap = kind == 0 ? &new_k : &new_v;
+      const CUtensorMap* nbmap = kind == 0 ? &newbox_k : &newbox_v;
+      auto load_rows_one_by_one = [&](uint32_t dst, uint32_t fb, int col, int pos0, int n) {
+        for (int i = 0; i < n; ++i) {
+          const int pos = pos0 + i;
+          if (pos < u.cached) tma_load_2d(dst + i * 128, gmap, fb, col, __ldg(slots + pos));
+          else tma_load_2d(dst + i * 128, nmap, fb, col, u.q_begin + pos - u.cached);
+        }
+      };
       for (int t = 0; t < u.n_tiles; ++t, ++tile_count) {
         const uint32_t stage = tile_count % kStages, phase = (tile_count / kStages) & 1;
         const int tile_begin = t * kBN;
@@ -209,42 +303,68 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
           const int n_instr = (kBN / rb) * 2;
           const int box = lane >> 1, half = lane & 1;
           const int pb = tile_begin + box * rb;
+          const bool old_box = pb + rb <= u.cached, new_box = pb >= u.cached;
           int first_slot = p.num_slots;
-          if (lane < n_instr && pb < u.kv_hi) first_slot = __ldg(slots + pb);
+          if (lane < n_instr && old_box) first_slot = __ldg(slots + pb);
           mbar_wait(bar(empty0 + stage), phase ^ 1);
+          flush_stage(stage);
           if (lane == 0) mbar_arrive_expect_tx(bar(full0 + stage), kTileBytes);
           __syncwarp();
-          if (lane < n_instr)
-            tma_load_2d(ring + stage * kTileBytes + half * kHalfBytes + box * rb * 128, bmap,
-                        bar(full0 + stage), col0 + half * 64, first_slot);
-        } else {
-          // gather mode: 32 row groups x 2 halves = 2 gather4 per lane
-          int4 rr[2];
-#pragma unroll
-          for (int it = 0; it < 2; ++it) {
-            const int grp = (lane >> 1) + it * 16;
-            const int pos0 = tile_begin + grp * 4;
-            if (pos0 + 3 < u.kv_hi) {
-              rr[it] = __ldg(reinterpret_cast<const int4*>(slots + pos0));
-            } else {
-              rr[it].x = pos0 + 0 < u.kv_hi ? __ldg(slots + pos0 + 0) : p.num_slots;
-              rr[it].y = pos0 + 1 < u.kv_hi ? __ldg(slots + pos0 + 1) : p.num_slots;
-              rr[it].z = pos0 + 2 < u.kv_hi ? __ldg(slots + pos0 + 2) : p.num_slots;
-              rr[it].w = pos0 + 3 < u.kv_hi ? __ldg(slots + pos0 + 3) : p.num_slots;
-            }
+          if (lane < n_instr) {
+            const uint32_t dst = ring + stage * kTileBytes + half * kHalfBytes + box * rb * 128;
+            const uint32_t fb = bar(full0 + stage);
+            const int col = col0 + half * 64;
+            if (old_box) tma_load_2d(dst, bmap, fb, col, first_slot);
+            else if (new_box) tma_load_2d(dst, nbmap, fb, col, u.q_begin + pb - u.cached);
+            else load_rows_one_by_one(dst, fb, col, pb, rb);  // the box straddling cached_len
           }
+        } else {
+          // gather mode: 32 row groups x 2 halves = 2 groups per lane
           mbar_wait(bar(empty0 + stage), phase ^ 1);
+          flush_stage(stage);
           if (lane == 0) mbar_arrive_expect_tx(bar(full0 + stage), kTileBytes);
           __syncwarp();
 #pragma unroll
           for (int it = 0; it < 2; ++it) {
             const int grp = (lane >> 1) + it * 16, half = lane & 1;
-            tma_gather4(ring + stage * kTileBytes + half * kHalfBytes + grp * 512, gmap, bar(full0 + stage),
-                        col0 + half * 64, rr[it].x, rr[it].y, rr[it].z, rr[it].w);
+            const int pos0 = tile_begin + grp * 4;
+            const uint32_t dst = ring + stage * kTileBytes + half * kHalfBytes + grp * 512;
+            const uint32_t fb = bar(full0 + stage);
+            const int col = col0 + half * 64;
+            if (pos0 + 4 <= u.cached) {
+              const int4 rr = __ldg(reinterpret_cast<const int4*>(slots + pos0));
+              tma_gather4(dst, gmap, fb, col, rr.x, rr.y, rr.z, rr.w);
+            } else if (pos0 >= u.cached) {
+              const int r0 = u.q_begin + pos0 - u.cached;
+              tma_gather4(dst, nmap, fb, col, r0, r0 + 1, r0 + 2, r0 + 3);
+            } else {
+              load_rows_one_by_one(dst, fb, col, pos0, 4);
+            }
           }
+        }
+        // tiles issued earlier may have landed by now
+        for (int s2 = 0; s2 < kStages; ++s2)
+          if (s2 != (int)stage) try_store(s2);
+        // does this tile hold rows this unit has to append?
+        const int lo = max(own_lo, tile_begin), hi = min(own_hi, tile_begin + kBN);
+        if (owner && lo < hi) {
+          pend[stage].valid = 1;
+          pend[stage].lo = lo;
+          pend[stage].hi = hi;
+          pend[stage].tile_begin = tile_begin;
+          pend[stage].col0 = col0;
+          pend[stage].phase = phase;
+          pend[stage].slots = slots;
         }
       }
     }
+    // tiles still waiting for their append: wait until they have landed, store, drain
+    for (int s = 0; s < kStages; ++s)
+      if (pend[s].valid == 1) {
+        mbar_wait(bar(full0 + s), pend[s].phase);
+        issue_stores(s);
+      }
+    bulk_wait0();
   } else if (warp == 2) {
     // ============================================================ UMMA issuer (one thread)
     if (lane == 0) {
@@ -336,7 +456,6 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
       const int vis_end = min(u.cached + q_row + 1, u.kv_len);  // keys [0, vis_end) are visible
       float m_used = -INFINITY, l_run = 0.f;
       for (int j = 0; j < u.n_tiles; ++j, ++my_tiles) {
-        const uint32_t tc = tile_count + j;
         const int tile_begin = j * kBN;
         mbar_wait(bar(kSFull + sub), my_tiles & 1);
         tc_fence_after_sync();
@@ -403,20 +522,6 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
         }
         m_used = m_new;
         const float m_sub = (m_used == -INFINITY) ? 0.f : m_used;
-        // ---- zero the V rows past the end of the request (page tails hold arbitrary bits)
-        {
-          const uint32_t stage = tc % kStages;
-          mbar_wait(bar(kFullV + stage), (tc / kStages) & 1);
-          const int n_valid = u.kv_len - tile_begin;
-          if (p.box_rows > 0 && n_valid < kBN && half == 0) {
-            uint8_t* vt = smem + Smem::vring + stage * kTileBytes;
-            for (int idx = row; idx < (kBN - n_valid) * 16; idx += 128) {
-              const int r2 = n_valid + (idx >> 4), c16 = idx & 15;
-              *reinterpret_cast<uint4*>(vt + (c16 >> 3) * kHalfBytes + r2 * 128 + (c16 & 7) * 16) = make_uint4(0, 0, 0, 0);
-            }
-            fence_proxy_async_smem();
-          }
-        }
         // ---- pass 2: P = exp2(S*scale - m), row sum, packed bf16 back to TMEM over my own S
         // columns (keys 0-63 -> columns 0-31, keys 64-127 -> columns 64-95 of the sub-tile)
         float l0 = 0.f, l1 = 0.f;
@@ -502,10 +607,11 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
 template <typename T>
 static int launch(const Params<T>& p, const void* q, int64_t q_rs, int64_t nnz, const void* k_cache,
                   const void* v_cache, cudaStream_t st) {
+  CUtensorMap nk, nv, nbk, nbv;
   const bool bf16 = std::is_same<T, __nv_bfloat16>::value;
   CUtensorMap mq, mk, mv, bk, bv;
   const uint64_t cols = (uint64_t)p.hkv * kD;
-  if (int rc = get_tensor_map_2d(&mq, q, nnz, (uint64_t)p.hq * kD, q_rs * 2, 64, kBM, bf16)) return rc;
+  if (int rc = encode_tensor_map_2d(&mq, q, nnz, (uint64_t)p.hq * kD, q_rs * 2, 64, kBM, bf16)) return rc;
   if (int rc = get_tensor_map_2d(&mk, k_cache, p.num_slots, cols, cols * 2, 64, 1, bf16)) return rc;
   if (int rc = get_tensor_map_2d(&mv, v_cache, p.num_slots, cols, cols * 2, 64, 1, bf16)) return rc;
   bk = mk;
@@ -514,6 +620,16 @@ static int launch(const Params<T>& p, const void* q, int64_t q_rs, int64_t nnz, 
     if (int rc = get_tensor_map_2d(&bk, k_cache, p.num_slots, cols, cols * 2, 64, p.box_rows, bf16)) return rc;
     if (int rc = get_tensor_map_2d(&bv, v_cache, p.num_slots, cols, cols * 2, 64, p.box_rows, bf16)) return rc;
   }
+  // the k / v inputs of this forward as [nnz, hkv*128] row-strided tensors (not cached: activations
+  // move between forwards)
+  if (int rc = encode_tensor_map_2d(&nk, p.k_new, nnz, cols, p.kv_rs * 2, 64, 1, bf16)) return rc;
+  if (int rc = encode_tensor_map_2d(&nv, p.v_new, nnz, cols, p.kv_rs * 2, 64, 1, bf16)) return rc;
+  nbk = nk;
+  nbv = nv;
+  if (p.box_rows > 0) {
+    if (int rc = encode_tensor_map_2d(&nbk, p.k_new, nnz, cols, p.kv_rs * 2, 64, p.box_rows, bf16)) return rc;
+    if (int rc = encode_tensor_map_2d(&nbv, p.v_new, nnz, cols, p.kv_rs * 2, 64, p.box_rows, bf16)) return rc;
+  }
   const size_t smem = Smem::total + 1024;
   static bool configured = false;
   if (!configured) {
@@ -521,16 +637,18 @@ static int launch(const Params<T>& p, const void* q, int64_t q_rs, int64_t nnz, 
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  attn_prefill_tc_kernel<T><<<num_sms(), kThreads, smem, st>>>(p, mq, mk, mv, bk, bv);
+  attn_prefill_tc_kernel<T><<<num_sms(), kThreads, smem, st>>>(p, mq, mk, mv, bk, bv, nk, nv, nbk, nbv);
   B200_POST_LAUNCH();
   return 0;
 }
 
 }  // namespace ptc
 
+extern std::atomic<int> g_prefill_skip_append;
+
 // entry used by b200_attn_prefill (attn_prefill.cu)
-int launch_prefill_tc(const void* q, int64_t q_rs, int64_t nnz, const void* k_cache, const void* v_cache,
-                      const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
+int launch_prefill_tc(const void* q, int64_t q_rs, int64_t nnz, const void* k, const void* v, int64_t kv_rs,
+                      void* k_cache, void* v_cache, const int32_t* out_loc, const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
                       const int32_t* cu_q, const int32_t* prefill_plan, int bs, int hq, int hkv,
                       int64_t num_slots, int page_size, float scale_log2, void* out, int dtype,
                       cudaStream_t st) {
@@ -546,7 +664,8 @@ int launch_prefill_tc(const void* q, int64_t q_rs, int64_t nnz, const void* k_ca
   }
 #define RUN(T_)                                                                                    \
   ptc::Params<T_> p{slot_table, st_stride, seq_lens, cu_q, prefill_plan, bs, hq, hkv, (int)num_slots, \
-                    box_rows, scale_log2, (T_*)out};                                               \
+                    box_rows, scale_log2, (T_*)out, (const T_*)k, (const T_*)v, kv_rs, (T_*)k_cache,  \
+                    (T_*)v_cache, out_loc, nnz, g_prefill_skip_append.load()};                                                   \
   return ptc::launch<T_>(p, q, q_rs, nnz, k_cache, v_cache, st)
   if (dtype == B200_DTYPE_BF16) {
     RUN(__nv_bfloat16);

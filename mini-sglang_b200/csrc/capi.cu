@@ -24,6 +24,8 @@ void set_error(const char* fmt, ...) {
 namespace b200 {
 std::atomic<int> g_decode_impl{1};
 std::atomic<int> g_prefill_impl{1};
+std::atomic<int> g_prefill_order{0};  // 0 = size-sorted + snake dealing (balanced; measured best), 1 = request-major
+std::atomic<int> g_prefill_skip_append{0};  // debug only
 std::atomic<int> g_decode_lookahead{4};
 std::atomic<int> g_decode_fused_combine{0};  // measured: the separate combine launch is ~5 us/layer cheaper than the in-kernel combiner warp
 }
@@ -32,6 +34,8 @@ extern "C" int b200_abi_version(void) { return 5; }
 
 extern "C" int b200_set_option(const char* name, int value) {
   if (name != nullptr && std::strcmp(name, "decode_impl") == 0) return b200::g_decode_impl.exchange(value);
+  if (name != nullptr && std::strcmp(name, "prefill_skip_append") == 0) return b200::g_prefill_skip_append.exchange(value);
+  if (name != nullptr && std::strcmp(name, "prefill_order") == 0) return b200::g_prefill_order.exchange(value);
   if (name != nullptr && std::strcmp(name, "prefill_impl") == 0) return b200::g_prefill_impl.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_lookahead") == 0) return b200::g_decode_lookahead.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_fused_combine") == 0) return b200::g_decode_fused_combine.exchange(value);

@@ -171,10 +171,32 @@ __global__ void __launch_bounds__(1024) meta_scan_kernel(const int32_t* __restri
 constexpr int kPrefillBins = 1024;
 __global__ void __launch_bounds__(1024) meta_prefill_plan_kernel(const int32_t* __restrict__ req_info,
                                                                  int bs, int32_t* __restrict__ plan,
-                                                                 int capacity) {
+                                                                 int capacity, int request_major) {
   __shared__ int hist[kPrefillBins];
   __shared__ int s_total;
+  __shared__ int sm[33];
   const int tid = threadIdx.x;
+  if (request_major) {
+    // request-major order (query tiles of a request adjacent, heaviest first): the units that share
+    // a request's K/V run at the same time on neighbouring CTAs, so the re-reads hit in L2
+    int carry = 0;
+    for (int base = 0; base < bs; base += 1024) {
+      const int r = base + tid;
+      int nq = 0;
+      if (r < bs) nq = (req_info[3 * r + 2] - req_info[3 * r + 1] + 127) / 128;
+      int tot;
+      const int incl = block_scan_incl(nq, sm, &tot);
+      const int start = carry + incl - nq;
+      if (r < bs && carry + tot <= capacity)
+        for (int qt = 0; qt < nq; ++qt) plan[4 + start + (nq - 1 - qt)] = r | (qt << 16);
+      carry += tot;
+    }
+    if (tid == 0) {
+      plan[0] = carry <= capacity ? carry : -1;
+      plan[1] = plan[2] = plan[3] = 0;
+    }
+    return;
+  }
   for (int i = tid; i < kPrefillBins; i += 1024) hist[i] = 0;
   if (tid == 0) s_total = 0;
   __syncthreads();
@@ -215,6 +237,9 @@ __global__ void __launch_bounds__(1024) meta_prefill_plan_kernel(const int32_t* 
 
 }  // namespace b200
 
+namespace b200 {
+extern std::atomic<int> g_prefill_order;
+}
 using namespace b200;
 
 extern "C" int b200_build_prefill_plan(const int32_t* req_info, int bs, int32_t* prefill_plan,
@@ -222,7 +247,7 @@ extern "C" int b200_build_prefill_plan(const int32_t* req_info, int bs, int32_t*
   B200_CHECK_ARG(bs > 0 && bs < 65536, "build_prefill_plan: batch size %d out of range", bs);
   B200_CHECK_ARG(capacity_items > 0 && prefill_plan != nullptr, "build_prefill_plan: no buffer");
   meta_prefill_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(req_info, bs, prefill_plan,
-                                                                  capacity_items);
+                                                                  capacity_items, g_prefill_order.load());
   B200_POST_LAUNCH();
   return 0;
 }

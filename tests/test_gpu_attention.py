@@ -168,7 +168,9 @@ def test_prefill_gqa_groups(b200, native_lib, hq, hkv, prefill_impl):
 
 def test_prefill_radix_shared_prefix_pages(b200, native_lib, prefill_impl):
     """Two requests whose leading page-table entries are identical (radix-shared pages)."""
-    rel = _run_case(b200, page_size=16, hq=16, hkv=8, lens=[(0, 300), (128, 260), (128, 400)],
+    # every sharer has the shared pages in its cached range: a prefix only becomes matchable after
+    # the forward that produced it (scheduler/cache.py cache_req), so nobody appends into them
+    rel = _run_case(b200, page_size=16, hq=16, hkv=8, lens=[(128, 300), (128, 260), (128, 400)],
                     phase="prefill", share_prefix=0)
     assert rel < 3e-3
 
@@ -334,3 +336,11 @@ def test_attention_against_flashinfer_golden(b200, native_lib, phase):
     bound = 1e-3 * scale + 2.0**-7 * want.abs() + 1e-6
     assert ((got - want).abs() <= bound).all(), ((got - want).abs() - bound).max()
     assert ((got - want).norm() / want.norm()).item() < 2.5e-3
+
+
+@pytest.mark.parametrize("page_size", [1, 16, 64])
+def test_prefill_unaligned_cached_boundary(b200, native_lib, page_size, prefill_impl):
+    """Chunked prefill leaves cached_len at arbitrary offsets (scheduler/prefill.py:126-151): the
+    K/V tile that straddles cached_len mixes pool rows and rows of this forward's k/v inputs."""
+    _run_case(b200, page_size=page_size, hq=16, hkv=8, lens=[(100, 300), (37, 200), (129, 130), (1, 140)],
+              phase="prefill")
