@@ -287,8 +287,6 @@ class AttentionPathRunner:
         self.pkg.ops.qknorm_rope_inplace(batch.positions, q, k, D, self.rotary._cos_sin_cache, self.qw, self.kw, EPS)
         o = self.backend.forward(q.view(n, self.hq, D), k, v, l, batch)
         self._last_out = o
-        if self.tp_group is not None:  # the reference's all-reduce after o_proj (linear.py:102-106)
-            torch.distributed.all_reduce(self.hidden[:n], group=self.tp_group)
 
     def capture(self, bs: int) -> None:
         if bs in self.graphs:
@@ -307,21 +305,9 @@ class AttentionPathRunner:
             self.stream.synchronize()
             g = torch.cuda.CUDAGraph()
             before = self.lib.b200_launch_count()
-            try:
-                with torch.cuda.graph(g, stream=self.stream):
-                    for l in range(L):
-                        self.layer(l, bs, batch)
-            except Exception as e:  # NCCL capture unsupported -> keep the attention path, drop the collective
-                if self.tp_group is None:
-                    raise
-                self.allreduce_note = f"all-reduce dropped from the graph: {type(e).__name__}"
-                self.tp_group = None
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                before = self.lib.b200_launch_count()
-                with torch.cuda.graph(g, stream=self.stream):
-                    for l in range(L):
-                        self.layer(l, bs, batch)
+            with torch.cuda.graph(g, stream=self.stream):
+                for l in range(L):
+                    self.layer(l, bs, batch)
             self.graph_launches[bs] = self.lib.b200_launch_count() - before
             self.last_out[bs] = self._last_out
         self.graphs[bs] = g
@@ -342,6 +328,12 @@ class AttentionPathRunner:
             self.backend.prepare_metadata(batch)
             self.backend.prepare_for_replay(batch)
             self.graphs[bs].replay()
+            if self.tp_group is not None:
+                # the reference's NCCL all-reduce of [nnz, hidden] after o_proj (layers/linear.py:102-106),
+                # one per layer; issued eagerly behind the replay (the o_proj GEMM between attention and
+                # the collective is outside the hot path, so nothing can be fused across it)
+                for _ in range(L):
+                    torch.distributed.all_reduce(self.hidden[:bs], group=self.tp_group)
             if host_copy:
                 out_h[:bs].copy_(self.last_out[bs].view(bs, -1), non_blocking=True)
         return len(triples)
@@ -357,6 +349,9 @@ def run_ours(args) -> dict:
     dev = torch.device("cuda", local_rank)
     tp_group = None
     if world > 1:
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ.get("B200_BENCH_WATCHDOG_S", "420")), exit=True)
         torch.distributed.init_process_group("nccl", device_id=dev)
         pkg.utils.set_tp_info(rank, world)
         tp_group = torch.distributed.group.WORLD if not args.no_allreduce else None
@@ -512,7 +507,7 @@ def run_ours(args) -> dict:
                                f"decode iterations sampled evenly over {sched.n_iters}",
                    "layers": L, "hq": HQ, "hkv": HKV, "head_dim": D, "page_size": args.page_size,
                    "parallelism": f"tp{world}" if world > 1 else "tp1", "cuda_graph": True,
-                   "allreduce": (runner.allreduce_note or ("nccl all-reduce [bs,1024] bf16 per layer" if world > 1 and not args.no_allreduce else "none")),
+                   "allreduce": ("nccl all-reduce [bs,1024] bf16 x 28 per step (eager, behind the graph replay)" if world > 1 and not args.no_allreduce else "none"),
                    "l2": "each layer reads its own pool slice; one step touches ~13 GB >> 126 MB L2",
                    "hbm_roofline_tokens_per_s": round(ceiling, 1)},
         "frac_of_hbm_roofline": round(value / ceiling, 4),
@@ -522,6 +517,9 @@ def run_ours(args) -> dict:
         "roofline": roofline, "prefill": prefill, "cpu_baseline": cpu, "clocks": clocks.summary(),
     }
     if world > 1:
+        import faulthandler
+
+        faulthandler.cancel_dump_traceback_later()
         torch.distributed.destroy_process_group()
     return res if rank == 0 else {}
 

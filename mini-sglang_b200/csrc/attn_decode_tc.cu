@@ -143,33 +143,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
   float* red = reinterpret_cast<float*>(smem + Smem::red);
   uint8_t* sUnits = smem + Smem::units;
 
-  const int chunk_tokens = p.plan[0];
-  const int total_units = p.plan[1] * p.hkv;
-  const int32_t* order = p.plan + kPlanHeader + p.bs + 1;
-  const int32_t* seq_lens = p.seq_lens;
-  // This CTA's k-th unit is position k*grid + (k even ? cta : grid-1-cta) of the size-sorted order
-  // ("snake" dealing): per-CTA work is balanced to within about one tile.
-  const int grid = gridDim.x, cta = blockIdx.x;
-  const int n_rounds = (total_units + grid - 1) / grid;
-  auto pos_of = [&](int k) { return k * grid + ((k & 1) ? grid - 1 - cta : cta); };
-
-  // ---------------------------------------------------------------- one-time setup
-  // every role walks the same unit list: decode it once, in parallel, into smem
-  for (int k = tid; k < kMaxUnitsSmem && k < n_rounds; k += kThreads) {
-    const int pos = pos_of(k);
-    Unit u;
-    u.n_tiles = -1;  // marks "no unit in this round"
-    if (pos < total_units) u = get_unit(pos, p.hkv, chunk_tokens, order, seq_lens);
-    *reinterpret_cast<Unit*>(sUnits + k * 40) = u;
-  }
-  auto unit_at = [&](int k) {
-    if (k < kMaxUnitsSmem) return *reinterpret_cast<const Unit*>(sUnits + k * 40);
-    const int pos = pos_of(k);
-    Unit u;
-    u.n_tiles = -1;
-    if (pos < total_units) u = get_unit(pos, p.hkv, chunk_tokens, order, seq_lens);
-    return u;
-  };
+  // ---------------------------------------------------------------- setup that touches no global memory
   // zero the operand buffers whose padding rows (heads >= G) are never written again
   for (int i = tid; i < (2 * kQBufBytes + 2 * kPBufBytes) / 16; i += kThreads)
     reinterpret_cast<uint4*>(smem + Smem::qbuf)[i] = make_uint4(0, 0, 0, 0);
@@ -198,12 +172,42 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     prefetch_tensormap(&box_v);
   }
   if (warp == kWarpQ) tmem_alloc(sbase + Smem::tmem_ptr, kTmemCols);
+  // PDL: everything above may overlap the tail of the previous kernel in the stream; from here on
+  // its results (and those of every kernel before it) are complete and visible.
+  pdl_wait();
+  pdl_launch_dependents();
+  const int chunk_tokens = p.plan[0];
+  const int total_units = p.plan[1] * p.hkv;
+  const int32_t* order = p.plan + kPlanHeader + p.bs + 1;
+  const int32_t* seq_lens = p.seq_lens;
+  // This CTA's k-th unit is position k*grid + (k even ? cta : grid-1-cta) of the size-sorted order
+  // ("snake" dealing): per-CTA work is balanced to within about one tile.
+  const int grid = gridDim.x, cta = blockIdx.x;
+  const int n_rounds = (total_units + grid - 1) / grid;
+  auto pos_of = [&](int k) { return k * grid + ((k & 1) ? grid - 1 - cta : cta); };
+
+  // ---------------------------------------------------------------- one-time setup
+  // every role walks the same unit list: decode it once, in parallel, into smem
+  for (int k = tid; k < kMaxUnitsSmem && k < n_rounds; k += kThreads) {
+    const int pos = pos_of(k);
+    Unit u;
+    u.n_tiles = -1;  // marks "no unit in this round"
+    if (pos < total_units) u = get_unit(pos, p.hkv, chunk_tokens, order, seq_lens);
+    *reinterpret_cast<Unit*>(sUnits + k * 40) = u;
+  }
+  auto unit_at = [&](int k) {
+    if (k < kMaxUnitsSmem) return *reinterpret_cast<const Unit*>(sUnits + k * 40);
+    const int pos = pos_of(k);
+    Unit u;
+    u.n_tiles = -1;
+    if (pos < total_units) u = get_unit(pos, p.hkv, chunk_tokens, order, seq_lens);
+    return u;
+  };
   fence_proxy_async_smem();  // zero-fill above must be visible to UMMA operand reads
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_s;
-
   if (warp < 4) {
     // ============================================================ TMA producers
     // K and V travel in separate rings (a K tile is dead as soon as QK^T has been issued, a V
@@ -634,10 +638,11 @@ static int launch_g(const Params<T>& p, const CUtensorMap& mk, const CUtensorMap
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  attn_decode_tc_kernel<T, G><<<num_sms(), kThreads, smem, st>>>(p, mk, mv, bk, bv);
+  B200_CHECK_CUDA(launch_pdl(attn_decode_tc_kernel<T, G>, dim3(num_sms()), dim3(kThreads), smem, st, p, mk, mv, bk, bv));
   B200_POST_LAUNCH();
   if (!p.fused_combine) {
-    attn_combine_kernel<T><<<dim3(p.bs, p.hq), kHeadDim, 0, st>>>(p.part_o, p.part_ml, p.plan, p.hq, p.out);
+    B200_CHECK_CUDA(launch_pdl(attn_combine_kernel<T>, dim3(p.bs, p.hq), dim3(kHeadDim), 0, st,
+                               (const float*)p.part_o, (const float*)p.part_ml, p.plan, p.hq, p.out));
     B200_POST_LAUNCH();
   }
   return 0;

@@ -22,6 +22,7 @@ void set_error(const char* fmt, ...) {
 }  // namespace b200
 
 namespace b200 {
+std::atomic<int> g_use_pdl{1};
 std::atomic<int> g_decode_impl{1};
 std::atomic<int> g_prefill_impl{1};
 std::atomic<int> g_prefill_order{0};  // 0 = size-sorted + snake dealing (balanced; measured best), 1 = request-major
@@ -33,6 +34,7 @@ std::atomic<int> g_decode_fused_combine{0};  // measured: the separate combine l
 extern "C" int b200_abi_version(void) { return 5; }
 
 extern "C" int b200_set_option(const char* name, int value) {
+  if (name != nullptr && std::strcmp(name, "use_pdl") == 0) return b200::g_use_pdl.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_impl") == 0) return b200::g_decode_impl.exchange(value);
   if (name != nullptr && std::strcmp(name, "prefill_skip_append") == 0) return b200::g_prefill_skip_append.exchange(value);
   if (name != nullptr && std::strcmp(name, "prefill_order") == 0) return b200::g_prefill_order.exchange(value);

@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(kHeadDim) attn_combine_kernel(const float* __r
                                                           const int32_t* __restrict__ plan, int hq,
                                                           T* __restrict__ out) {
   const int r = blockIdx.x, hh = blockIdx.y, d = threadIdx.x;
+  pdl_wait();                // the decode kernel's partials
+  pdl_launch_dependents();   // the next kernel may start its prologue
   const int32_t* chunk_start = plan + kPlanHeader;
   const int n = chunk_start[r + 1] - chunk_start[r];
   if (n <= 1) return;

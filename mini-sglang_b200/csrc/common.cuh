@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <utility>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -50,6 +51,25 @@ inline int num_sms() {
     if (cached <= 0) cached = 148;
   }
   return cached;
+}
+
+extern std::atomic<int> g_use_pdl;
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl.load() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 template <typename T>
@@ -155,6 +175,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its
+// predecessor in the stream is still running; it must execute pdl_wait() before it reads anything
+// the predecessor writes or writes anything the predecessor (or ITS predecessors) may still read.
+// Every PDL kernel of this library waits before its first global write, so completion stays
+// transitive along the stream.  pdl_launch_dependents() lets the successor begin its prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 __device__ __forceinline__ float fast_exp2(float x) {

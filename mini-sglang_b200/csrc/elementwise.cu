@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(
     int hq, int hkv, int64_t qrs, int64_t krs) {
   constexpr int kDim = G * 8;
   constexpr int kHalf = kDim / 2;
+  pdl_wait();
+  pdl_launch_dependents();
   const int heads = hq + hkv;
   const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int j = threadIdx.x % G;
@@ -292,9 +294,9 @@ static int launch_qknorm_rope_g(void* q, void* k, const void* qw, const void* kw
   const int g = d / 8;
   const int64_t threads = nnz * (hq + hkv) * g;
   dim3 grid((unsigned)ceil_div<int64_t>(threads, 256)), block(256);
-#define L(G_)                                                                                    \
-  qknorm_rope_kernel<T, PosT, G_, kNorm><<<grid, block, 0, st>>>(                                \
-      (T*)q, (T*)k, (const T*)qw, (const T*)kw, eps, (const PosT*)pos, cs, nnz, hq, hkv, qrs, krs)
+#define L(G_)                                                                                        \
+  B200_CHECK_CUDA(launch_pdl(qknorm_rope_kernel<T, PosT, G_, kNorm>, grid, block, 0, st, (T*)q, (T*)k, \
+                             (const T*)qw, (const T*)kw, eps, (const PosT*)pos, cs, nnz, hq, hkv, qrs, krs))
   if (g == 8) L(8);
   else if (g == 16) L(16);
   else if (g == 32) L(32);
