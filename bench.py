@@ -138,6 +138,24 @@ def effective_cpus() -> int:
     return max(1, min(n, 64))
 
 
+def load_ncu_traffic() -> dict:
+    """DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_ncu_decode_tc_summary.json: one launch of tools/microbench.py decode, iteration 500)."""
+    p = ROOT / "profiles" / "r01_ncu_decode_tc_summary.json"
+    try:
+        d = json.loads(p.read_text())
+
+        def mb(key):
+            val, unit = d[key].split()[:2]
+            return float(val) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+
+        return {"traffic": int(mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")),
+                "traffic_alg_bytes": 133917 * 4096 + 128 * (2 * 8 * 256 + 2 * 16 * 256),
+                "traffic_source": "profiles/r01_ncu_decode_tc_summary.json (ncu --set full, decode iteration 500, bs=128)"}
+    except Exception:
+        return {"traffic": None}
+
+
 def load_peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -456,9 +474,9 @@ def run_ours(args) -> dict:
             n_launch += L
             del ag
     achieved = alg_bytes / (attn_ms * 1e-3) / 1e9
-    roofline = {"kernel": "attn_decode_kernel(+combine)", "bound": "hbm", "achieved": round(achieved, 1),
+    roofline = {"kernel": "attn_decode_tc_kernel(+combine)", "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
-                "peak_source": peaks["source"], "traffic": None,
+                "peak_source": peaks["source"], **load_ncu_traffic(),
                 "alg_bytes_per_launch": int(alg_bytes / n_launch), "us_per_launch": round(attn_ms * 1e3 / n_launch, 2)}
 
     # ---------------- prefill TFLOP/s over the schedule's prompt batches
