@@ -105,6 +105,10 @@ __global__ void __launch_bounds__(1024) meta_scan_kernel(const int32_t* __restri
   const int total_kv = carry_k;
   const int max_kv = s_max;
   int chunk = (total_kv + target_items - 1) / target_items;
+  // With enough requests to give every persistent CTA several work units (target_items / 2 of them
+  // is ~3 per CTA) splitting buys nothing: the size-sorted snake order balances whole requests, and
+  // unsplit requests need no partial (o, m, l) round trip and no combine work.
+  if (2 * bs >= target_items) chunk = max_kv;
   const int min_chunk = (max_kv + kMaxSplits - 1) / kMaxSplits;
   if (chunk < min_chunk) chunk = min_chunk;
   chunk = ((chunk + 127) / 128) * 128;  // whole 128-token tiles

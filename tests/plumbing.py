@@ -32,7 +32,7 @@ class TinyModel:
 
 def run_generation(model: TinyModel, ctx, backend, make_req: Callable, make_batch: Callable,
                    prompts: List[List[int]], out_len: int, page_size: int, pre_attention: Callable,
-                   free_pages: List[int]):
+                   free_pages: List[int], forced=None, hidden_trace=None):
     """Prefill all prompts in one batch, then `out_len - 1` decode steps. Returns generated ids
     [n_seqs, out_len] and the last-step hidden states (fp32) for numeric comparison."""
     dev = model.device
@@ -65,6 +65,10 @@ def run_generation(model: TinyModel, ctx, backend, make_req: Callable, make_batc
         logits = (h @ model.lm_head).float()
         nxt = logits.argmax(-1).tolist()
         hidden_last = h.float().cpu()
+        if hidden_trace is not None:
+            hidden_trace.append(hidden_last)
+        if forced is not None:  # teacher forcing: follow another run's tokens, compare hidden states
+            nxt = [int(t) for t in forced[:, step]]
         for i, r in enumerate(reqs):
             generated[i].append(nxt[i])
             tokens[i].append(nxt[i])
