@@ -45,7 +45,11 @@ B200_API int b200_device_supported(void);
  *   "decode_impl": 1 = tcgen05 + TMA kernel (default), 0 = cp.async / CUDA-core kernel.
  *   "prefill_impl": 1 = tcgen05 kernel (default, needs prefill_plan), 0 = mma.sync bring-up kernel.
  *   "decode_lookahead": S^T buffers the UMMA issuer may run ahead (2..4, default 4).
- *   "decode_fused_combine": 1 = merge split-KV partials inside the decode launch, 0 = combine kernel (default).
+ *   "decode_fused_combine": 0 = separate combine launch, 1 = merge split-KV partials inside the decode
+ *       launch, 2 = auto (default): in-kernel, and no combine launch, exactly when the plan policy
+ *       leaves the batch unsplit.
+ *   "decode_plan_target": when splitting, aim at target * CTA-hint / kv_heads (request, chunk) items (default 2).
+ *   "decode_plan_nosplit": no split-KV once bs * kv_heads * 100 >= value * CTA-hint (default 75; 0 = always split).
  * Returns the previous value, or -1 for an unknown name. */
 B200_API int b200_set_option(const char* name, int value);
 
@@ -60,6 +64,21 @@ B200_API int b200_store_kv(void* k_cache, void* v_cache, int64_t cache_row_strid
                   const void* k, const void* v, int64_t input_row_stride_bytes,
                   const void* indices, int idx64, int64_t num_tokens, int64_t row_bytes,
                   void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2  Row gather (SURVEY 8f "next": embedding lookup and last-token gather).  Replaces
+ *     `indexing(weights, indices, output=, vocab_range=)` (M/kernel/index.py:32-53 ->
+ *     M/kernel/csrc/jit/index.cu:34-96; caller VocabParallelEmbedding.forward,
+ *     M/layers/embedding.py:31-41) and `x[indices].contiguous()` (M/layers/embedding.py:92-94).
+ *     out[t] = weights[indices[t]], rows of `row_bytes` bytes (multiple of 16), strides in bytes.
+ *     vocab_length >= 0 selects the masked form: pos = indices[t] - vocab_start; rows with
+ *     pos outside [0, vocab_length) are zero-filled (the reference's masked_index_kernel).
+ *     vocab_length < 0: plain gather; like the reference, indices are not range-checked.
+ * ------------------------------------------------------------------------------------- */
+B200_API int b200_index_rows(const void* weights, int64_t weight_row_stride_bytes, const void* indices,
+                    int idx64, int64_t num_indices, int64_t row_bytes, void* out,
+                    int64_t out_row_stride_bytes, int64_t vocab_start, int64_t vocab_length,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K7  RMSNorm.  Replaces flashinfer.rmsnorm(x, w, eps, out=...) at M/layers/norm.py:16-21

@@ -14,7 +14,7 @@ from typing import Optional
 _LIB: Optional[C.CDLL] = None
 LIB_PATH = Path(__file__).resolve().parent / "libb200attn.so"
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _i32, _i64, _f32, _vp, _sz = C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
 
@@ -26,6 +26,7 @@ SIGNATURES = {
     "b200_device_supported": (_i32, []),
     "b200_set_option": (_i32, [C.c_char_p, _i32]),
     "b200_store_kv": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i32, _i64, _i64, _vp]),
+    "b200_index_rows": (_i32, [_vp, _i64, _vp, _i32, _i64, _i64, _vp, _i64, _i64, _i64, _vp]),
     "b200_rmsnorm": (
         _i32,
         [_vp, _vp, _vp, _i64, _i32, _i32, _i64, _i64, _i64, _i64, _f32, _i32, _vp],

@@ -22,6 +22,7 @@ STAMP = PKG_DIR / ".libb200attn.stamp"
 SOURCES = [
     "capi.cu",
     "elementwise.cu",
+    "index_rows.cu",
     "metadata.cu",
     "attn_decode.cu",
     "attn_decode_tc.cu",

@@ -679,6 +679,7 @@ static int launch(const Params<T>& p, cudaStream_t st) {
 
 extern std::atomic<int> g_decode_lookahead;
 extern std::atomic<int> g_decode_fused_combine;
+bool decode_plan_is_unsplit(int bs, int num_kv_heads, int ctas);  // metadata.cu
 
 // entry used by b200_attn_decode (attn_decode.cu)
 int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, const void* v,
@@ -687,6 +688,10 @@ int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, c
                      const int32_t* plan, int bs, int hq, int hkv, int64_t num_slots, int page_size,
                      float scale_log2, void* out, float* part_o, float* part_ml, int* counters,
                      int dtype, cudaStream_t st) {
+  // A batch the plan policy leaves unsplit needs no combine pass: run the in-kernel merge (a no-op
+  // then; still correct for a foreign plan that does split) and skip the combine launch.
+  int fused = g_decode_fused_combine.load();
+  if (fused == 2) fused = decode_plan_is_unsplit(bs, hkv, 2 * num_sms()) ? 1 : 0;
   int num_s = g_decode_lookahead.load();
   if (num_s < 2) num_s = 2;
   if (num_s > dtc::kNumS) num_s = dtc::kNumS;
@@ -704,7 +709,7 @@ int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, c
 #define RUN(T_)                                                                                   \
   dtc::Params<T_> p{(const T_*)q, q_rs, (const T_*)k, k_rs, (const T_*)v, v_rs, (T_*)k_cache,     \
                     (T_*)v_cache, out_loc, slot_table, st_stride, seq_lens, plan, bs, hq, hkv,    \
-                    (int)num_slots, box_rows, num_s, g_decode_fused_combine.load(), scale_log2, (T_*)out,  \
+                    (int)num_slots, box_rows, num_s, fused, scale_log2, (T_*)out,  \
                     part_o, part_ml, counters};                       \
   return dtc::launch<T_>(p, st)
   if (dtype == B200_DTYPE_BF16) {

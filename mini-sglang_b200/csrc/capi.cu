@@ -28,10 +28,16 @@ std::atomic<int> g_prefill_impl{1};
 std::atomic<int> g_prefill_order{0};  // 0 = size-sorted + snake dealing (balanced; measured best), 1 = request-major
 std::atomic<int> g_prefill_skip_append{0};  // debug only
 std::atomic<int> g_decode_lookahead{4};
-std::atomic<int> g_decode_fused_combine{0};  // measured: the separate combine launch is ~5 us/layer cheaper than the in-kernel combiner warp
+// Split-KV policy (measured, profiles/r01_decode_plan_sweep.json): splitting costs a partial (o, m, l)
+// round trip plus the combine pass, so it only pays when whole requests cannot fill the grid.
+std::atomic<int> g_decode_plan_target{2};    // when splitting, aim at target * CTA-hint / kv_heads (request, chunk) items
+std::atomic<int> g_decode_plan_nosplit{75};  // no split once bs * kv_heads * 100 >= nosplit * CTA-hint (0 = always split)
+// 0 = separate combine launch, 1 = the last-arriving CTA merges the partials in the decode launch,
+// 2 = auto: in-kernel (and no combine launch at all) exactly when the policy above does not split.
+std::atomic<int> g_decode_fused_combine{2};
 }
 
-extern "C" int b200_abi_version(void) { return 5; }
+extern "C" int b200_abi_version(void) { return 6; }
 
 extern "C" int b200_set_option(const char* name, int value) {
   if (name != nullptr && std::strcmp(name, "use_pdl") == 0) return b200::g_use_pdl.exchange(value);
@@ -40,6 +46,8 @@ extern "C" int b200_set_option(const char* name, int value) {
   if (name != nullptr && std::strcmp(name, "prefill_order") == 0) return b200::g_prefill_order.exchange(value);
   if (name != nullptr && std::strcmp(name, "prefill_impl") == 0) return b200::g_prefill_impl.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_lookahead") == 0) return b200::g_decode_lookahead.exchange(value);
+  if (name != nullptr && std::strcmp(name, "decode_plan_target") == 0) return b200::g_decode_plan_target.exchange(value);
+  if (name != nullptr && std::strcmp(name, "decode_plan_nosplit") == 0) return b200::g_decode_plan_nosplit.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_fused_combine") == 0) return b200::g_decode_fused_combine.exchange(value);
   return -1;
 }

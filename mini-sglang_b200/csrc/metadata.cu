@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(1024) meta_scan_kernel(const int32_t* __restri
                                                          int32_t* __restrict__ cu_q,
                                                          int32_t* __restrict__ cu_k,
                                                          int32_t* __restrict__ plan,
-                                                         int target_items) {
+                                                         int target_items, int nosplit) {
   __shared__ int sm[33];
   __shared__ int s_max;
   const int tid = threadIdx.x;
@@ -105,10 +105,10 @@ __global__ void __launch_bounds__(1024) meta_scan_kernel(const int32_t* __restri
   const int total_kv = carry_k;
   const int max_kv = s_max;
   int chunk = (total_kv + target_items - 1) / target_items;
-  // With enough requests to give every persistent CTA several work units (target_items / 2 of them
-  // is ~3 per CTA) splitting buys nothing: the size-sorted snake order balances whole requests, and
-  // unsplit requests need no partial (o, m, l) round trip and no combine work.
-  if (2 * bs >= target_items) chunk = max_kv;
+  // With enough whole requests to fill the persistent grid splitting buys nothing: the size-sorted
+  // snake order balances them, and unsplit requests need no partial (o, m, l) round trip and no
+  // combine work (the host decides from bs alone, so the launcher can drop the combine launch).
+  if (nosplit) chunk = max_kv;
   const int min_chunk = (max_kv + kMaxSplits - 1) / kMaxSplits;
   if (chunk < min_chunk) chunk = min_chunk;
   chunk = ((chunk + 127) / 128) * 128;  // whole 128-token tiles
@@ -243,6 +243,8 @@ __global__ void __launch_bounds__(1024) meta_prefill_plan_kernel(const int32_t* 
 
 namespace b200 {
 extern std::atomic<int> g_prefill_order;
+extern std::atomic<int> g_decode_plan_target;
+extern std::atomic<int> g_decode_plan_nosplit;
 }
 using namespace b200;
 
@@ -259,6 +261,14 @@ extern "C" int b200_build_prefill_plan(const int32_t* req_info, int bs, int32_t*
 extern "C" size_t b200_decode_plan_ints(int bs) {
   return (size_t)kPlanHeader + (size_t)bs + 1 + (size_t)kMaxSplits * bs;
 }
+
+namespace b200 {
+// the one place that decides "this batch is not split" -- shared with the decode launcher
+bool decode_plan_is_unsplit(int bs, int num_kv_heads, int ctas) {
+  const int pct = g_decode_plan_nosplit.load();
+  return pct > 0 && (int64_t)bs * num_kv_heads * 100 >= (int64_t)pct * ctas;
+}
+}  // namespace b200
 
 extern "C" int b200_build_metadata(const int32_t* req_info, int bs, const int32_t* page_table,
                                    int64_t page_table_stride, int32_t* seq_lens,
@@ -284,10 +294,10 @@ extern "C" int b200_build_metadata(const int32_t* req_info, int bs, const int32_
     B200_POST_LAUNCH();
   }
   const int ctas = num_ctas_hint > 0 ? num_ctas_hint : 2 * num_sms();
-  int target = (ctas * 6) / num_kv_heads;
+  int target = (ctas * g_decode_plan_target.load()) / num_kv_heads;
   if (target < 1) target = 1;
   meta_scan_kernel<<<1, 1024, 0, st>>>(req_info, bs, seq_lens, cu_seqlens_q, cu_seqlens_k,
-                                       decode_plan, target);
+                                       decode_plan, target, decode_plan_is_unsplit(bs, num_kv_heads, ctas) ? 1 : 0);
   B200_POST_LAUNCH();
   return 0;
 }

@@ -212,3 +212,16 @@ def patch_minisgl_layers(model: Any) -> int:
             children = [c for c in vars(obj).values() if not callable(c) or hasattr(c, "__dict__")]
         stack.extend(children)
     return count
+
+
+def patch_minisgl_kernels() -> bool:
+    """Point ``minisgl.kernel.indexing`` at the sm_100a row gather.  ``VocabParallelEmbedding.forward``
+    imports the function from ``minisgl.kernel`` at call time (reference layers/embedding.py:32-34),
+    so re-binding the package attribute is enough; no reference edit.  Returns False when the
+    reference package is not importable (nothing to patch)."""
+    try:
+        import minisgl.kernel as ref_kernel
+    except Exception:
+        return False
+    ref_kernel.indexing = ops.indexing
+    return True

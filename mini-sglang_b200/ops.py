@@ -5,6 +5,7 @@ meaning, backed by the sm_100a kernels through the C ABI.
 reference call site                                     function here
 =====================================================  =====================================
 ``minisgl.kernel.store_cache`` (kernel/store.py:30)      :func:`store_cache`
+``minisgl.kernel.indexing`` (kernel/index.py:32)         :func:`indexing`
 ``flashinfer.rmsnorm`` (layers/norm.py:10,16-21)         :func:`rmsnorm`
 ``flashinfer.fused_add_rmsnorm`` (layers/norm.py:25,36)  :func:`fused_add_rmsnorm`
 ``flashinfer.apply_rope_with_cos_sin_cache_inplace``     :func:`apply_rope_with_cos_sin_cache_inplace`
@@ -18,7 +19,7 @@ nothing synchronises.  CPU tensors raise -- there is no fallback.
 
 from __future__ import annotations
 
-from typing import Optional
+from typing import Optional, Tuple
 
 import torch
 
@@ -92,6 +93,44 @@ def store_cache(
         ),
         "b200_store_kv",
     )
+
+
+def indexing(
+    weights: torch.Tensor,
+    indices: torch.Tensor,
+    *,
+    output: Optional[torch.Tensor] = None,
+    vocab_range: Optional[Tuple[int, int]] = None,  # (start, length)
+) -> torch.Tensor:
+    """``output[t] = weights[indices[t]]`` -- the reference's ``indexing`` (kernel/index.py:32-53), used
+    by ``VocabParallelEmbedding.forward`` (layers/embedding.py:31-41).  With ``vocab_range = (start,
+    length)`` rows whose ``indices[t] - start`` falls outside ``[0, length)`` are zero (the TP-sharded
+    vocabulary).  ``weights``: ``[rows, dim]`` with contiguous rows (row stride free); ``indices``:
+    int32 / int64 ``[n]``.  Also serves the last-token gather ``x[indices].contiguous()``
+    (layers/embedding.py:92-94)."""
+    _require_cuda(weights, indices, output)
+    if weights.dim() != 2 or weights.stride(1) != 1:
+        raise RuntimeError("indexing: weights must be 2-D with a contiguous last dimension")
+    if indices.dtype not in (torch.int32, torch.int64) or indices.dim() != 1 or not indices.is_contiguous():
+        raise RuntimeError("indexing: indices must be a contiguous int32/int64 vector")
+    n = indices.shape[0]
+    if output is None:
+        output = weights.new_empty(n, weights.shape[1])
+    if output.shape != (n, weights.shape[1]) or output.dtype != weights.dtype or output.stride(1) != 1:
+        raise RuntimeError("indexing: output must be [len(indices), dim] of the weights' dtype")
+    es = weights.element_size()
+    start, length = (0, -1) if vocab_range is None else (int(vocab_range[0]), int(vocab_range[1]))
+    if vocab_range is not None and (length < 0 or length > weights.shape[0]):
+        raise RuntimeError("indexing: vocab_range length must lie in [0, rows of weights]")
+    _cabi.check(
+        _cabi.load().b200_index_rows(
+            weights.data_ptr(), weights.stride(0) * es, indices.data_ptr(),
+            1 if indices.dtype == torch.int64 else 0, n, weights.shape[1] * es, output.data_ptr(),
+            output.stride(0) * es, start, length, _stream_ptr(weights),
+        ),
+        "b200_index_rows",
+    )
+    return output
 
 
 def rmsnorm(

@@ -286,7 +286,7 @@ def test_decode_full_size_properties(b200, native_lib, decode_impl):
     rc = lib.b200_build_metadata(info.data_ptr(), bs, gw.ctx.page_table.data_ptr(), gw.ctx.page_table.stride(0),
                                  md.cache_seqlens.data_ptr(), md.cu_seqlens_q.data_ptr(), md.cu_seqlens_k.data_ptr(),
                                  md.page_table.data_ptr(), md.page_table.stride(0), md.page_table.shape[1],
-                                 md.decode_plan.data_ptr(), hkv, 1024, torch.cuda.current_stream().cuda_stream)
+                                 md.decode_plan.data_ptr(), hkv, 8192, torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     out2 = gw.backend.forward(qg.view(-1, hq, d), kg, vg, 0, batch)
     torch.cuda.synchronize()

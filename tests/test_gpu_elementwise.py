@@ -4,6 +4,7 @@ import torch
 
 from oracle import norm as o_norm
 from oracle import rope as o_rope
+from oracle.index import ref_indexing
 from oracle.store import ref_store_kv
 
 pytestmark = pytest.mark.gpu

@@ -11,6 +11,7 @@ from oracle import attention as o_attn
 from oracle import metadata as o_meta
 from oracle import norm as o_norm
 from oracle import rope as o_rope
+from oracle.index import ref_indexing
 from oracle.store import ref_store_kv, ref_store_kv_bytes
 
 GOLDEN = json.loads((Path(__file__).parent / "golden" / "metadata_golden.json").read_text())
@@ -63,6 +64,35 @@ def test_store_oracle_is_a_byte_scatter():
     want = ref_store_kv_bytes(kb, idx.numpy(), k.contiguous().view(torch.uint8).numpy())
     assert np.array_equal(kc.view(64, -1).view(torch.uint8).numpy(), want)
     assert torch.equal(vc[idx.long()].view(9, -1), v)
+
+
+def _reference_known_answer_indexing(weights, indices, vocab_range=None):
+    """The reference's own checker for its index kernel (tests/kernel/test_index.py:13-29)."""
+    import torch.nn.functional as F
+
+    if vocab_range is None:
+        return F.embedding(indices, weights)
+    start, length = vocab_range
+    indices = indices - start
+    mask = (indices < 0) | (indices >= length)
+    indices = indices.masked_fill(mask, 0)
+    result = F.embedding(indices, weights)
+    result[mask] = 0
+    return result
+
+
+@pytest.mark.parametrize("idx_dtype", [torch.int32, torch.int64])
+@pytest.mark.parametrize("vocab_range", [None, (1000, 1000), (0, 4000), (3000, 1000)])
+def test_index_oracle_matches_reference_known_answer(idx_dtype, vocab_range):
+    torch.manual_seed(5)
+    vocab, dim = 4000, 256
+    rows = vocab if vocab_range is None else vocab_range[1]
+    w = torch.randn(rows, dim).to(torch.float16)
+    for n in (1, 7, 512):
+        idx = torch.randint(0, vocab, (n,), dtype=idx_dtype)
+        got = ref_indexing(w, idx, vocab_range)
+        want = _reference_known_answer_indexing(w, idx.long(), vocab_range)
+        assert torch.equal(got.view(torch.int16), want.view(torch.int16))
 
 
 def test_attention_oracle_against_naive_loops():
