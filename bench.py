@@ -278,6 +278,12 @@ class AttentionPathRunner:
         self.stream = torch.cuda.Stream(device=device)
         self.backend.init_capture_graph(self.max_seq, graph_bs_list())
         self.lib = pkg._cabi.load()
+        # e2e leg: pipelined host -> device staging
+        self.copy_stream = torch.cuda.Stream(device)
+        self.staging = None
+        self.stg_ready = [torch.cuda.Event() for _ in range(2)]
+        self.stg_free = [torch.cuda.Event() for _ in range(2)]
+        self._e2e_step = 0
 
     # ---- batch objects
     def make_batch(self, triples, phase, pad=True):
@@ -337,9 +343,24 @@ class AttentionPathRunner:
         pos_h, loc_h = self.host_inputs(batch)
         with torch.cuda.stream(self.stream):
             if host_copy:
+                # Host inputs of this step go up on a copy stream into one of two staging buffers, so
+                # the upload of step i+1 overlaps the attention of step i (the engine / scheduler
+                # stream split of the reference, scheduler.py:53-55,102); the compute stream then
+                # moves them into the graph's static buffers device to device.
                 qkv_h, out_h = host_bufs
-                for l in range(L):
-                    self.qkv[l, :bs].copy_(qkv_h[l, :bs], non_blocking=True)
+                slot = self._e2e_step % 2
+                self._e2e_step += 1
+                if self.staging is None:
+                    self.staging = [torch.empty_like(self.qkv) for _ in range(2)]
+                stg = self.staging[slot]
+                self.copy_stream.wait_event(self.stg_free[slot])
+                with torch.cuda.stream(self.copy_stream):
+                    for l in range(L):
+                        stg[l, :bs].copy_(qkv_h[l, :bs], non_blocking=True)
+                    self.stg_ready[slot].record(self.copy_stream)
+                self.stream.wait_event(self.stg_ready[slot])
+                self.qkv[:, :bs].copy_(stg[:, :bs])
+                self.stg_free[slot].record(self.stream)
             self.positions[:bs].copy_(pos_h, non_blocking=True)
             self.out_loc[:bs].copy_(loc_h, non_blocking=True)
             batch.positions, batch.out_loc = self.positions[:bs], self.out_loc[:bs]
@@ -447,6 +468,7 @@ def run_ours(args) -> dict:
     alg_bytes = 0
     attn_ms = 0.0
     n_launch = 0
+    per_step = []  # [padded bs, us per layer, fraction of the HBM peak] of every timed step
     with torch.cuda.stream(runner.stream):
         for tr in step_triples:
             batch = runner.make_batch(tr, "decode")
@@ -469,15 +491,19 @@ def run_ours(args) -> dict:
             ag.replay()
             a1.record()
             a1.synchronize()
-            attn_ms += a0.elapsed_time(a1)
-            alg_bytes += L * decode_bytes_per_layer([(r.table_idx, r.cached_len, r.device_len) for r in batch.padded_reqs], hq, hkv)
+            step_ms = a0.elapsed_time(a1)
+            step_bytes = L * decode_bytes_per_layer([(r.table_idx, r.cached_len, r.device_len) for r in batch.padded_reqs], hq, hkv)
+            attn_ms += step_ms
+            alg_bytes += step_bytes
+            per_step.append([bs, round(step_ms * 1e3 / L, 1), round(step_bytes / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 3)])
             n_launch += L
             del ag
     achieved = alg_bytes / (attn_ms * 1e-3) / 1e9
     roofline = {"kernel": "attn_decode_tc_kernel(+combine)", "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
                 "peak_source": peaks["source"], **load_ncu_traffic(),
-                "alg_bytes_per_launch": int(alg_bytes / n_launch), "us_per_launch": round(attn_ms * 1e3 / n_launch, 2)}
+                "alg_bytes_per_launch": int(alg_bytes / n_launch), "us_per_launch": round(attn_ms * 1e3 / n_launch, 2),
+                "per_step_bs_us_frac": per_step}
 
     # ---------------- prefill TFLOP/s over the schedule's prompt batches
     prefill = None
@@ -509,6 +535,28 @@ def run_ours(args) -> dict:
                    "frac_of_bf16_peak": round(tf / peaks["bf16_tflops"], 4), "peak_tflops": peaks["bf16_tflops"],
                    "tokens": sum(sched.in_lens), "batches": len(sched.prefill_batches())}
 
+    # ---------------- row gather (embedding lookup of one prompt batch; table >> L2)
+    gather = None
+    if not args.skip_prefill:
+        with torch.cuda.stream(runner.stream):
+            table = torch.randn((151936, 1024), device=dev, dtype=torch.bfloat16)  # Qwen3-0.6B embedding: vocab x hidden
+            ids = torch.randint(0, table.shape[0], (16384,), device=dev, dtype=torch.int32)
+            outb = torch.empty((ids.numel(), table.shape[1]), device=dev, dtype=torch.bfloat16)
+            for _ in range(3):
+                pkg.ops.indexing(table, ids, output=outb)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            g0.record()
+            for _ in range(reps):
+                pkg.ops.indexing(table, ids, output=outb)
+            g1.record()
+            g1.synchronize()
+            us = g0.elapsed_time(g1) * 1e3 / reps
+            gbytes = 2 * outb.numel() * 2 + ids.numel() * 4
+            gather = {"kernel": "index_rows_kernel", "rows": ids.numel(), "row_bytes": table.shape[1] * 2, "us": round(us, 2),
+                      "GBs": round(gbytes / us / 1e3, 1), "frac_of_hbm_peak": round(gbytes / us / 1e3 / peaks["hbm_gbs"], 3)}
+            del table, outb
+
     # ---------------- CPU baseline (oracle, bounded sample) + parity on the bench workload
     cpu = None
     if rank == 0 and not args.skip_cpu:
@@ -532,7 +580,7 @@ def run_ours(args) -> dict:
         "e2e": {"value": round(e2e_value, 1), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d / args.steps),
                 "d2h_bytes_per_step": int(d2h / args.steps), "ms_per_step": round(e2e_ms / args.steps, 4)},
         "gpu_launches": int(eager_launches + graph_launches),
-        "roofline": roofline, "prefill": prefill, "cpu_baseline": cpu, "clocks": clocks.summary(),
+        "roofline": roofline, "prefill": prefill, "index_rows": gather, "cpu_baseline": cpu, "clocks": clocks.summary(),
     }
     if world > 1:
         import faulthandler

@@ -62,6 +62,67 @@ def test_store_rejects_bad_args(b200, native_lib):
         b200.ops.store_cache(kc.cpu(), kc.cpu(), torch.zeros(2, dtype=torch.int32), kc[:2].cpu(), kc[:2].cpu())
 
 
+def test_indexing_reference_golden_shape(b200, native_lib):
+    """The reference's own tests (tests/kernel/test_index.py:32-99): fp16 table with 4096-wide rows,
+    int32 indices, bs = 2^0 .. 2^15, plain and masked to the vocabulary shard of rank 1 of 4."""
+    import torch.nn.functional as F
+
+    EMBED, TOKENS, TP = 4096, 32768, 4
+    g = torch.Generator(device="cuda").manual_seed(0)
+    weights = torch.randn((TOKENS, EMBED), device="cuda", dtype=torch.float16, generator=g)
+    shard = TOKENS // TP
+    for bs in [2**n for n in range(0, 16)]:
+        indices = torch.randint(0, TOKENS, (bs,), device="cuda", dtype=torch.int32, generator=g)
+        assert torch.all(b200.ops.indexing(weights, indices) == F.embedding(indices.long(), weights)), bs
+        got = b200.ops.indexing(weights[:shard], indices, vocab_range=(shard, shard))
+        pos = indices.long() - shard
+        mask = (pos < 0) | (pos >= shard)
+        want = F.embedding(pos.masked_fill(mask, 0), weights[:shard])
+        want[mask] = 0
+        assert torch.all(got == want), bs
+
+
+@pytest.mark.parametrize("idx_dtype", [torch.int32, torch.int64])
+@pytest.mark.parametrize("dim,dtype", [(1024, torch.bfloat16), (128, torch.bfloat16), (5120, torch.float16), (8, torch.bfloat16)])
+def test_indexing_matches_oracle_bitwise(b200, native_lib, idx_dtype, dim, dtype):
+    """Bit-exact vs the oracle: plain, masked (incl. ids below the shard start, which wrap as unsigned),
+    empty input, caller-provided output, row-strided table, and the last-token gather use."""
+    torch.manual_seed(2)
+    vocab = 3001
+    w = torch.randn(vocab, dim).to(dtype)
+    wg = w.cuda()
+    bits = torch.int16
+    for n in (0, 1, 33, 2500):
+        idx = torch.randint(0, vocab, (n,), dtype=idx_dtype)
+        got = b200.ops.indexing(wg, idx.cuda())
+        assert got.shape == (n, dim)
+        assert torch.equal(got.cpu().view(bits), ref_indexing(w, idx).view(bits))
+        for rng in ((1000, 750), (0, vocab), (2900, 101)):
+            shard = w[rng[0] : rng[0] + rng[1]]
+            out = torch.full((n, dim), 7.0, dtype=dtype, device="cuda")
+            ret = b200.ops.indexing(wg[rng[0] : rng[0] + rng[1]], idx.cuda(), output=out, vocab_range=rng)
+            assert ret.data_ptr() == out.data_ptr()
+            assert torch.equal(out.cpu().view(bits), ref_indexing(shard, idx, rng).view(bits))
+    # row-strided table (a column slice of a wider matrix) and the LM-head gather x[last_indices]
+    if dim >= 16:
+        wide = torch.randn(257, 2 * dim).to(dtype)
+        idx = torch.randint(0, 257, (64,), dtype=idx_dtype)
+        got = b200.ops.indexing(wide.cuda()[:, dim:], idx.cuda())
+        assert torch.equal(got.cpu().view(bits), wide[:, dim:][idx.long()].contiguous().view(bits))
+
+
+def test_indexing_rejects_bad_args(b200, native_lib):
+    w = torch.zeros(16, 128, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        b200.ops.indexing(w, torch.zeros(2, dtype=torch.int16, device="cuda"))
+    with pytest.raises(RuntimeError):
+        b200.ops.indexing(w, torch.zeros(2, dtype=torch.int32, device="cuda"), output=torch.zeros(3, 128, device="cuda", dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError):
+        b200.ops.indexing(w.cpu(), torch.zeros(2, dtype=torch.int32))
+    with pytest.raises(RuntimeError):  # rows of 4 * 2 = 8 bytes: not a multiple of 16
+        b200.ops.indexing(torch.zeros(16, 4, device="cuda", dtype=torch.bfloat16), torch.zeros(2, dtype=torch.int32, device="cuda"))
+
+
 @pytest.mark.parametrize("rows,dim", [(1, 1024), (37, 1024), (256, 5120), (19, 8192), (5, 4096), (3, 2048 + 64)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_rmsnorm_rows(b200, native_lib, rows, dim, dtype):
