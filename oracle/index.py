@@ -28,6 +28,8 @@ def ref_indexing(
     """CPU tensors in, fresh ``[n, dim]`` tensor of the weights' dtype out (bit-exact rows)."""
     assert weights.device.type == "cpu" and weights.dim() == 2
     n = indices.numel()
+    if n == 0:
+        return weights.new_empty(0, weights.shape[1])
     es = weights.element_size()
     w_bytes = weights.contiguous().view(torch.uint8).numpy().reshape(weights.shape[0], weights.shape[1] * es)
     idx = indices.to(torch.int64).numpy()
