@@ -48,6 +48,8 @@ B200_API int b200_device_supported(void);
  *   "decode_fused_combine": 0 = separate combine launch, 1 = merge split-KV partials inside the decode
  *       launch, 2 = auto (default): in-kernel, and no combine launch, exactly when the plan policy
  *       leaves the batch unsplit.
+ *   "decode_defer_epilogue": 1 (default) = a decode unit's epilogue runs after the next unit's first
+ *       tile has been handed to the tensor core; 0 = strictly unit after unit.
  *   "decode_plan_target": when splitting, aim at target * CTA-hint / kv_heads (request, chunk) items (default 2).
  *   "decode_plan_nosplit": no split-KV once bs * kv_heads * 100 >= value * CTA-hint (default 75; 0 = always split).
  * Returns the previous value, or -1 for an unknown name. */

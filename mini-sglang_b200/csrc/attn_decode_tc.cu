@@ -66,8 +66,8 @@ struct Smem {
   static constexpr int pbuf = qbuf + 2 * kQBufBytes;
   static constexpr int bars = pbuf + 2 * kPBufBytes;      // 32 mbarriers
   static constexpr int tmem_ptr = bars + 32 * 8;
-  static constexpr int red = tmem_ptr + 16;               // [2][4][16] floats (tile max), [4][16] (sums)
-  static constexpr int units = red + (2 * 4 * 16 + 4 * 16 + 4 * 16) * 4;  // decoded work units
+  static constexpr int red = tmem_ptr + 16;               // floats: [2][4][16] tile max, [2][4][16] row sums, [2][4][16] new-token dots
+  static constexpr int units = red + (2 * 4 * 16 + 2 * 4 * 16 + 2 * 4 * 16) * 4;  // decoded work units
   static constexpr int total = units + kMaxUnitsSmem * 40;
 };
 enum Bar { kFullK = 0, kEmptyK = 3, kFullV = 6, kEmptyV = 9, kSFull = 12, kPFull = 16, kOFull = 18, kQFull = 20, kQEmpty = 22, kFinFull = 24, kFinEmpty = 28 };
@@ -93,6 +93,7 @@ struct Params {
   int box_rows;  // rows per tiled TMA box (8..64, divides page_size); 0 = gather4 mode
   int num_s;     // S^T buffers in use (2..kNumS)
   int fused_combine;  // 1: last-arriving unit merges the split-KV partials in this launch
+  int defer;          // 1: a unit's epilogue runs after the next unit's first P^T has been issued
   float scale_log2;
   T* out;
   float* part_o;
@@ -397,41 +398,156 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     const int ct = tid - 128;          // 0..127 = TMEM lane = key within tile = output dim
     const int cw = warp - 4;           // TMEM lane quadrant of this warp
     const uint32_t lane_base = (uint32_t)(cw * 32) << 16;
-    float* red_max = red;              // [2][4][16]
-    float* red_sum = red + 2 * 4 * 16; // [4][16]
-    float* red_new = red_sum + 4 * 16; // [4][16]
-    uint32_t tile_count = 0, fin_count = 0;
-    for (int k = 0; k < n_rounds; ++k) {
-      const Unit u = unit_at(k);
-      if (u.n_tiles < 0) continue;  // no unit for this CTA in the last round
-      float acc[G], l_thr[G], m_run[G], alpha_prev[G], q_new[G];
-      float kn = 0.f, vn = 0.f;
+    float* red_max = red;              // [2][4][16], by tile parity
+    uint32_t tile_count = 0, fin_count = 0, unit_par = 0;
+    // State of one unit's online softmax; everything the epilogue needs.
+    struct UnitState {
+      Unit u;
+      float l_thr[G], m_run[G], q_new[G], alpha_last[G];
+      float kn, vn;
+      int app_loc;
+      Vec8 app_x;
+      uint32_t last_tc;
+    };
+    float acc[G];  // O^T accumulator (thread = output dim); one unit at a time owns it
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = 0.f;
+
+    // acc = acc * a + O^T of tile tc (waits for that tile's PV MMA)
+    auto retire = [&](uint32_t tc, const float (&a)[G]) {
+      mbar_wait(bar(kOFull + (tc & 1)), (tc >> 1) & 1);
+      tc_fence_after_sync();
+      uint32_t o[16];
+      tmem_ld_x16(tmem_base + lane_base + kNumS * kNPad + (tc & 1) * kNPad, o);
+      tmem_wait_ld();
+#pragma unroll
+      for (int g = 0; g < G; ++g) acc[g] = acc[g] * a[g] + __uint_as_float(o[g]);
+    };
+
+    // Unit epilogue on CUDA cores: row sums, the appended token (score, value, pool append), output.
+    auto finish = [&](UnitState& st) {
+      const Unit& u = st.u;
+      // reduction scratch double buffered by unit parity: the next unit may write its slots while
+      // stragglers still read this unit's (every unit passes a named barrier in between)
+      float* red_sum = red + 2 * 4 * 16 + unit_par * 64;  // [4][16]
+      float* red_new = red + 4 * 4 * 16 + unit_par * 64;  // [4][16]
+      unit_par ^= 1;
+      float pnew[G];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        acc[g] = 0.f;
-        l_thr[g] = 0.f;
-        m_run[g] = -INFINITY;
-        alpha_prev[g] = 0.f;
-        q_new[g] = 0.f;
+        const float ls = warp_sum(st.l_thr[g]);
+        float sn = 0.f;
+        if (u.last_chunk) sn = warp_sum(st.q_new[g] * st.kn);
+        if (lane == 0) {
+          red_sum[cw * 16 + g] = ls;
+          red_new[cw * 16 + g] = sn;
+        }
+      }
+      named_bar_sync(1, 128);
+      float l_tot[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        l_tot[g] = red_sum[g] + red_sum[16 + g] + red_sum[32 + g] + red_sum[48 + g];
+        pnew[g] = 0.f;
+      }
+      if (u.last_chunk) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float s_new = (red_new[g] + red_new[16 + g] + red_new[32 + g] + red_new[48 + g]) * p.scale_log2;
+          const float m_new = fmaxf(st.m_run[g], s_new);
+          const float a = fast_exp2(st.m_run[g] - m_new);
+          pnew[g] = fast_exp2(s_new - m_new);
+          acc[g] = acc[g] * a + pnew[g] * st.vn;
+          l_tot[g] = l_tot[g] * a + pnew[g];
+          st.m_run[g] = m_new;
+        }
+        // fused KV append: this head's new K and V rows go into the pool (operands fetched at unit start)
+        if (ct < 32) {
+          T* dst = (ct < 16 ? p.k_cache : p.v_cache) + (int64_t)st.app_loc * p.hkv * kD + u.h * kD + (ct & 15) * 8;
+          *reinterpret_cast<Vec8*>(dst) = st.app_x;
+        }
+      }
+      // ---- write out
+      if (u.n_chunks == 1) {
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          p.out[((int64_t)u.r * p.hq + u.h * G + g) * kD + ct] = DTypeTraits<T>::from_float(acc[g] / l_tot[g]);
+      } else {
+        const int64_t base = ((int64_t)u.r * kMaxSplits + u.c) * p.hq + u.h * G;
+#pragma unroll
+        for (int g = 0; g < G; ++g) p.part_o[(base + g) * kD + ct] = acc[g];
+        if (ct < G) {
+          // m_run / l_tot are uniform across threads; thread g stores head g's pair
+          float mm = 0.f, ll = 0.f;
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+            if (g == ct) {
+              mm = st.m_run[g];
+              ll = l_tot[g];
+            }
+          p.part_ml[(base + ct) * 2 + 0] = mm;
+          p.part_ml[(base + ct) * 2 + 1] = ll;
+        }
+        // ---- hand the unit to the combiner warp (asynchronous split-KV merge): the softmax warps
+        // only pay an mbarrier arrive; the release/acquire pair orders the partial stores above
+        // before the combiner's device-scope fence + arrival counter.
+        if (p.fused_combine) {
+          const uint32_t slot = fin_count % kFinRing;
+          mbar_wait(bar(kFinEmpty + slot), ((fin_count / kFinRing) & 1) ^ 1);
+          mbar_arrive(bar(kFinFull + slot));
+          ++fin_count;
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) acc[g] = 0.f;
+    };
+
+    // The last tile of a unit is retired, and the unit's epilogue run, only AFTER the first P^T of
+    // the next unit has been handed to the tensor core (p.defer): the PV latency of the last tile
+    // and the epilogue then overlap the next unit's first PV instead of idling the pipe.
+    UnitState cur, old;
+    bool pending = false;
+    for (int k = 0; k < n_rounds; ++k) {
+      cur.u = unit_at(k);
+      const Unit& u = cur.u;
+      if (u.n_tiles < 0) continue;  // no unit for this CTA in the last round
+      cur.kn = 0.f;
+      cur.vn = 0.f;
+      cur.app_loc = 0;
+      cur.app_x = Vec8{{0u, 0u, 0u, 0u}};
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        cur.l_thr[g] = 0.f;
+        cur.m_run[g] = -INFINITY;
+        cur.alpha_last[g] = 0.f;
+        cur.q_new[g] = 0.f;
       }
       if (u.last_chunk) {
         // operands of the appended token's score / value: issue the loads now, use them in the
         // epilogue -- their latency hides behind the tile loop
         const T* qrow = p.q + (int64_t)u.r * p.q_rs + (int64_t)(u.h * G) * kD + ct;
 #pragma unroll
-        for (int g = 0; g < G; ++g) q_new[g] = DTypeTraits<T>::to_float(qrow[g * kD]);
-        kn = DTypeTraits<T>::to_float(p.k_new[(int64_t)u.r * p.k_rs + u.h * kD + ct]);
-        vn = DTypeTraits<T>::to_float(p.v_new[(int64_t)u.r * p.v_rs + u.h * kD + ct]);
+        for (int g = 0; g < G; ++g) cur.q_new[g] = DTypeTraits<T>::to_float(qrow[g * kD]);
+        cur.kn = DTypeTraits<T>::to_float(p.k_new[(int64_t)u.r * p.k_rs + u.h * kD + ct]);
+        cur.vn = DTypeTraits<T>::to_float(p.v_new[(int64_t)u.r * p.v_rs + u.h * kD + ct]);
+        // fused KV append (threads 0-15: K row, 16-31: V row, 16 bytes each): destination slot and
+        // payload are fetched here as well, so the epilogue only issues the store
+        if (ct < 32) {
+          cur.app_loc = p.out_loc[u.r];
+          const T* src = ct < 16 ? p.k_new + (int64_t)u.r * p.k_rs : p.v_new + (int64_t)u.r * p.v_rs;
+          cur.app_x = *reinterpret_cast<const Vec8*>(src + u.h * kD + (ct & 15) * 8);
+        }
       }
-      auto accumulate_o = [&](uint32_t tc) {
-        mbar_wait(bar(kOFull + (tc & 1)), (tc >> 1) & 1);
-        tc_fence_after_sync();
-        uint32_t o[16];
-        tmem_ld_x16(tmem_base + lane_base + kNumS * kNPad + (tc & 1) * kNPad, o);
-        tmem_wait_ld();
-#pragma unroll
-        for (int g = 0; g < G; ++g) acc[g] = acc[g] * alpha_prev[g] + __uint_as_float(o[g]);
-      };
+      if (u.n_tiles == 0) {
+        // nothing for the tensor core (the unit is just the appended token)
+        if (pending) {
+          retire(old.last_tc, old.alpha_last);
+          finish(old);
+          pending = false;
+        }
+        finish(cur);
+        continue;
+      }
       for (int j = 0; j < u.n_tiles; ++j) {
         const uint32_t tc = tile_count + j;
         mbar_wait(bar(kSFull + tc % p.num_s), (tc / p.num_s) & 1);
@@ -466,101 +582,40 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const float mt = fmaxf(fmaxf(rm[g], rm[16 + g]), fmaxf(rm[32 + g], rm[48 + g]));
-          const float m_new = fmaxf(m_run[g], mt);  // finite: every tile has >= 1 valid key
-          alpha[g] = fast_exp2(m_run[g] - m_new);
+          const float m_new = fmaxf(cur.m_run[g], mt);  // finite: every tile has >= 1 valid key
+          alpha[g] = fast_exp2(cur.m_run[g] - m_new);
           const float pv = fast_exp2(sv[g] - m_new);
-          l_thr[g] = l_thr[g] * alpha[g] + pv;
-          m_run[g] = m_new;
+          cur.l_thr[g] = cur.l_thr[g] * alpha[g] + pv;
+          cur.m_run[g] = m_new;
           *reinterpret_cast<T*>(pdst + (g >> 3) * 2048 + (ct >> 3) * 128 + (g & 7) * 16 + (ct & 7) * 2) =
               DTypeTraits<T>::from_float(pv);
         }
         fence_proxy_async_smem();   // P^T visible to the tensor core
         tc_fence_before_sync();     // our tcgen05.ld of S^T is ordered before the next QK overwrite
         mbar_arrive(bar(kPFull + (tc & 1)));
-        if (j > 0) accumulate_o(tc - 1);
+        if (j > 0) {
+          retire(tc - 1, cur.alpha_last);
+        } else if (pending) {
+          retire(old.last_tc, old.alpha_last);
+          finish(old);
+          pending = false;
+        }
 #pragma unroll
-        for (int g = 0; g < G; ++g) alpha_prev[g] = alpha[g];
+        for (int g = 0; g < G; ++g) cur.alpha_last[g] = alpha[g];
       }
-      if (u.n_tiles > 0) accumulate_o(tile_count + u.n_tiles - 1);
       tile_count += u.n_tiles;
-
-      // ---- per-unit reductions on CUDA cores: row sums, and the appended token
-      float pnew[G];
-      {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const float ls = warp_sum(l_thr[g]);
-          float sn = 0.f;
-          if (u.last_chunk) sn = warp_sum(q_new[g] * kn);
-          if (lane == 0) {
-            red_sum[cw * 16 + g] = ls;
-            red_new[cw * 16 + g] = sn;
-          }
-        }
-        named_bar_sync(1, 128);
-      }
-      float l_tot[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        l_tot[g] = red_sum[g] + red_sum[16 + g] + red_sum[32 + g] + red_sum[48 + g];
-        pnew[g] = 0.f;
-      }
-      if (u.last_chunk) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const float s_new = (red_new[g] + red_new[16 + g] + red_new[32 + g] + red_new[48 + g]) * p.scale_log2;
-          const float m_new = fmaxf(m_run[g], s_new);
-          const float a = fast_exp2(m_run[g] - m_new);
-          pnew[g] = fast_exp2(s_new - m_new);
-          acc[g] = acc[g] * a + pnew[g] * vn;
-          l_tot[g] = l_tot[g] * a + pnew[g];
-          m_run[g] = m_new;
-        }
-        // fused KV append: copy this head's new K and V rows into the pool
-        if (ct < 32) {
-          const int64_t dst = (int64_t)p.out_loc[u.r] * p.hkv * kD + u.h * kD;
-          const int cc = ct & 15;
-          if (ct < 16) {
-            const Vec8 x = *reinterpret_cast<const Vec8*>(p.k_new + (int64_t)u.r * p.k_rs + u.h * kD + cc * 8);
-            *reinterpret_cast<Vec8*>(p.k_cache + dst + cc * 8) = x;
-          } else {
-            const Vec8 x = *reinterpret_cast<const Vec8*>(p.v_new + (int64_t)u.r * p.v_rs + u.h * kD + cc * 8);
-            *reinterpret_cast<Vec8*>(p.v_cache + dst + cc * 8) = x;
-          }
-        }
-      }
-      named_bar_sync(1, 128);  // red_sum / red_new are reused by the next unit
-      // ---- write out
-      if (u.n_chunks == 1) {
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-          p.out[((int64_t)u.r * p.hq + u.h * G + g) * kD + ct] = DTypeTraits<T>::from_float(acc[g] / l_tot[g]);
+      cur.last_tc = tile_count - 1;
+      if (p.defer) {
+        old = cur;
+        pending = true;
       } else {
-        const int64_t base = ((int64_t)u.r * kMaxSplits + u.c) * p.hq + u.h * G;
-#pragma unroll
-        for (int g = 0; g < G; ++g) p.part_o[(base + g) * kD + ct] = acc[g];
-        if (ct < G) {
-          // m_run / l_tot are uniform across threads; thread g stores head g's pair
-          float mm = 0.f, ll = 0.f;
-#pragma unroll
-          for (int g = 0; g < G; ++g)
-            if (g == ct) {
-              mm = m_run[g];
-              ll = l_tot[g];
-            }
-          p.part_ml[(base + ct) * 2 + 0] = mm;
-          p.part_ml[(base + ct) * 2 + 1] = ll;
-        }
-        // ---- hand the unit to the combiner warp (asynchronous split-KV merge): the softmax warps
-        // only pay an mbarrier arrive; the release/acquire pair orders the partial stores above
-        // before the combiner's device-scope fence + arrival counter.
-        if (p.fused_combine) {
-          const uint32_t slot = fin_count % kFinRing;
-          mbar_wait(bar(kFinEmpty + slot), ((fin_count / kFinRing) & 1) ^ 1);
-          mbar_arrive(bar(kFinFull + slot));
-          ++fin_count;
-        }
+        retire(cur.last_tc, cur.alpha_last);
+        finish(cur);
       }
+    }
+    if (pending) {
+      retire(old.last_tc, old.alpha_last);
+      finish(old);
     }
   } else if (warp == kWarpCombine) {
     // ============================================================ split-KV combiner (one warp)
@@ -679,6 +734,7 @@ static int launch(const Params<T>& p, cudaStream_t st) {
 
 extern std::atomic<int> g_decode_lookahead;
 extern std::atomic<int> g_decode_fused_combine;
+extern std::atomic<int> g_decode_defer;
 bool decode_plan_is_unsplit(int bs, int num_kv_heads, int ctas);  // metadata.cu
 
 // entry used by b200_attn_decode (attn_decode.cu)
@@ -709,7 +765,7 @@ int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, c
 #define RUN(T_)                                                                                   \
   dtc::Params<T_> p{(const T_*)q, q_rs, (const T_*)k, k_rs, (const T_*)v, v_rs, (T_*)k_cache,     \
                     (T_*)v_cache, out_loc, slot_table, st_stride, seq_lens, plan, bs, hq, hkv,    \
-                    (int)num_slots, box_rows, num_s, fused, scale_log2, (T_*)out,  \
+                    (int)num_slots, box_rows, num_s, fused, g_decode_defer.load(), scale_log2, (T_*)out,  \
                     part_o, part_ml, counters};                       \
   return dtc::launch<T_>(p, st)
   if (dtype == B200_DTYPE_BF16) {

@@ -35,6 +35,7 @@ std::atomic<int> g_decode_plan_nosplit{75};  // no split once bs * kv_heads * 10
 // 0 = separate combine launch, 1 = the last-arriving CTA merges the partials in the decode launch,
 // 2 = auto: in-kernel (and no combine launch at all) exactly when the policy above does not split.
 std::atomic<int> g_decode_fused_combine{2};
+std::atomic<int> g_decode_defer{1};  // unit epilogue deferred behind the next unit's first tile
 }
 
 extern "C" int b200_abi_version(void) { return 6; }
@@ -48,6 +49,7 @@ extern "C" int b200_set_option(const char* name, int value) {
   if (name != nullptr && std::strcmp(name, "decode_lookahead") == 0) return b200::g_decode_lookahead.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_plan_target") == 0) return b200::g_decode_plan_target.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_plan_nosplit") == 0) return b200::g_decode_plan_nosplit.exchange(value);
+  if (name != nullptr && std::strcmp(name, "decode_defer_epilogue") == 0) return b200::g_decode_defer.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_fused_combine") == 0) return b200::g_decode_fused_combine.exchange(value);
   return -1;
 }

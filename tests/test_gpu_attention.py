@@ -12,13 +12,17 @@ from oracle import metadata as o_meta
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 0], ids=["tcgen05", "cpasync"])
+@pytest.fixture(params=[1, 0, 2], ids=["tcgen05", "cpasync", "tcgen05-inorder"])
 def decode_impl(request, b200, native_lib):
-    """Both decode kernels are held to the same oracle: the tcgen05 + TMA-gather4 product kernel
-    and the cp.async / CUDA-core bring-up kernel (selected with the debug option)."""
-    prev = b200._cabi.set_option("decode_impl", request.param)
-    yield request.param
+    """Both decode kernels are held to the same oracle: the tcgen05 + TMA product kernel (with the
+    unit epilogue deferred behind the next unit's first tile -- the default -- and strictly in
+    order) and the cp.async / CUDA-core bring-up kernel (selected with the debug options)."""
+    impl = 0 if request.param == 0 else 1
+    prev = b200._cabi.set_option("decode_impl", impl)
+    prev_defer = b200._cabi.set_option("decode_defer_epilogue", 0 if request.param == 2 else 1)
+    yield impl
     b200._cabi.set_option("decode_impl", prev)
+    b200._cabi.set_option("decode_defer_epilogue", prev_defer)
 
 
 def _check_metadata(md, ref: o_meta.RefMetadata, page_size: int):
