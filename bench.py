@@ -381,6 +381,10 @@ class AttentionPathRunner:
 def run_ours(args) -> dict:
     pkg = importlib.import_module("mini-sglang_b200")
     pkg.build_native()
+    for o in args.opt:
+        name, val = o.split("=")
+        if pkg._cabi.set_option(name, int(val)) == -1:
+            raise SystemExit(f"unknown option {name}")
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -696,6 +700,7 @@ def main() -> None:
     ap.add_argument("--skip-prefill", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--no-allreduce", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="name=value for b200_set_option (A/B experiments)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
