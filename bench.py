@@ -336,11 +336,18 @@ class AttentionPathRunner:
             self.last_out[bs] = self._last_out
         self.graphs[bs] = g
 
-    def decode_step(self, triples, host_copy: bool = False, host_bufs=None) -> int:
-        """prepare_metadata + replay on self.stream. Returns number of real tokens."""
+    def schedule_step(self, triples):
+        """What the reference's scheduler hands to the path for one decode iteration (outside the
+        timed region, like the scheduler thread): the Batch of Reqs and the pinned host positions /
+        out_loc (scheduler.py:204-259)."""
         batch = self.make_batch(triples, "decode")
-        bs = batch.padded_size
         pos_h, loc_h = self.host_inputs(batch)
+        return batch, pos_h, loc_h, len(triples)
+
+    def decode_step(self, step, host_copy: bool = False, host_bufs=None) -> int:
+        """H2D of the step's inputs + prepare_metadata + replay on self.stream. Returns number of real tokens."""
+        batch, pos_h, loc_h, n_tokens = step
+        bs = batch.padded_size
         with torch.cuda.stream(self.stream):
             if host_copy:
                 # Host inputs of this step go up on a copy stream into one of two staging buffers, so
@@ -375,7 +382,7 @@ class AttentionPathRunner:
                     torch.distributed.all_reduce(self.hidden[:bs], group=self.tp_group)
             if host_copy:
                 out_h[:bs].copy_(self.last_out[bs].view(bs, -1), non_blocking=True)
-        return len(triples)
+        return n_tokens
 
 
 def run_ours(args) -> dict:
@@ -417,8 +424,10 @@ def run_ours(args) -> dict:
         torch.cuda.synchronize()
 
     # ---------------- device-timed value
-    for it in warm_iters:
-        runner.decode_step(sched.live(it))
+    steps = [runner.schedule_step(tr) for tr in step_triples]
+    warm_steps = [runner.schedule_step(sched.live(it)) for it in warm_iters]
+    for st in warm_steps:
+        runner.decode_step(st)
     barrier()
     launches0 = lib.b200_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -426,8 +435,8 @@ def run_ours(args) -> dict:
     with ClockSampler(local_rank) as clocks:
         with torch.cuda.stream(runner.stream):
             ev0.record()
-        for tr in step_triples:
-            tokens += runner.decode_step(tr)
+        for st in steps:
+            tokens += runner.decode_step(st)
         with torch.cuda.stream(runner.stream):
             ev1.record()
         barrier()
@@ -444,15 +453,15 @@ def run_ours(args) -> dict:
     qkv_h = torch.empty((L, NUM_SEQS, runner.width), dtype=torch.bfloat16).pin_memory()
     qkv_h.copy_(runner.qkv.cpu())
     out_h = torch.empty((NUM_SEQS, hq * D), dtype=torch.bfloat16).pin_memory()
-    for it in warm_iters[:2]:
-        runner.decode_step(sched.live(it), True, (qkv_h, out_h))
+    for st in warm_steps[:2]:
+        runner.decode_step(st, True, (qkv_h, out_h))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h2d = d2h = 0
     with torch.cuda.stream(runner.stream):
         e0.record()
-    for tr in step_triples:
-        runner.decode_step(tr, True, (qkv_h, out_h))
+    for st, tr in zip(steps, step_triples):
+        runner.decode_step(st, True, (qkv_h, out_h))
         bs = next(b for b in graph_bs_list() if b >= len(tr))
         h2d += L * bs * runner.width * 2 + bs * 8 + bs * 12
         d2h += bs * hq * D * 2
