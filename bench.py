@@ -115,6 +115,15 @@ def prefill_flops_per_layer(triples, hq=HQ) -> int:
     return 4 * hq * D * tot
 
 
+def prefill_bytes_per_layer(triples, hq=HQ, hkv=HKV) -> int:
+    """Algorithmic HBM bytes of one prefill launch: q read + o written (nnz * 2*Hq*D*2), this forward's
+    k, v read and appended (nnz * 2 * 2*Hkv*D*2), cached prefix K/V read once per kv head
+    (sum cached * 2*Hkv*D*2).  K/V tiles shared by the q tiles of a request are counted once."""
+    nnz = sum(d - c for (_, c, d) in triples)
+    cached = sum(c for (_, c, _) in triples)
+    return nnz * 2 * hq * D * 2 + nnz * 2 * 2 * hkv * D * 2 + cached * 2 * hkv * D * 2
+
+
 def graph_bs_list(max_bs: int = 256) -> List[int]:
     return [1, 2, 4] + list(range(8, max_bs + 1, 8))  # engine/graph.py:67
 
@@ -525,7 +534,7 @@ def run_ours(args) -> dict:
         p_ms = 0.0
         with torch.cuda.stream(runner.stream):
             for rep in range(2):  # first pass = warm-up
-                flops, p_ms = 0, 0.0
+                flops, p_ms, p_bytes = 0, 0.0, 0
                 for tr in sched.prefill_batches():
                     batch = runner.make_batch(tr, "prefill")
                     pos_h, loc_h = runner.host_inputs(batch)
@@ -543,9 +552,17 @@ def run_ours(args) -> dict:
                     p1.synchronize()
                     p_ms += p0.elapsed_time(p1)
                     flops += L * prefill_flops_per_layer(tr, hq)
+                    p_bytes += L * prefill_bytes_per_layer(tr, hq, hkv)
         tf = flops / (p_ms * 1e-3) / 1e12
+        # cfg1's prompts are short (avg 558 tokens, GQA 2): the launch is bounded by HBM about as much
+        # as by the tensor pipe, so both floors are reported
+        t_tensor = flops / (peaks["bf16_tflops"] * 1e12) * 1e3
+        t_hbm = p_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3
         prefill = {"tflops": round(tf, 1), "ms": round(p_ms, 2), "flops": flops,
                    "frac_of_bf16_peak": round(tf / peaks["bf16_tflops"], 4), "peak_tflops": peaks["bf16_tflops"],
+                   "alg_bytes": p_bytes, "GBs": round(p_bytes / (p_ms * 1e-3) / 1e9, 1),
+                   "tensor_floor_ms": round(t_tensor, 2), "hbm_floor_ms": round(t_hbm, 2),
+                   "frac_of_roofline": round(max(t_tensor, t_hbm) / p_ms, 4),
                    "tokens": sum(sched.in_lens), "batches": len(sched.prefill_batches())}
 
     # ---------------- row gather (embedding lookup of one prompt batch; table >> L2)
