@@ -35,6 +35,9 @@ extern "C" {
 
 /* ABI version of this header (bumped on any signature change). */
 B200_API int b200_abi_version(void);
+/* sha256 of the sources + flags this binary was built from (mini-sglang_b200/build.py compares it with
+ * the tree to decide whether a rebuild is needed; a stale binary can therefore never pass as current). */
+B200_API const char* b200_build_digest(void);
 /* Thread-local description of the last non-zero return. */
 B200_API const char* b200_last_error(void);
 /* Number of kernels this library has launched so far (bench.py's gpu_launches). */

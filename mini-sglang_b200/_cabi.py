@@ -14,13 +14,14 @@ from typing import Optional
 _LIB: Optional[C.CDLL] = None
 LIB_PATH = Path(__file__).resolve().parent / "libb200attn.so"
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _i32, _i64, _f32, _vp, _sz = C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
 
 # name -> (restype, argtypes); mirrors include/b200attn.h one to one
 SIGNATURES = {
     "b200_abi_version": (_i32, []),
+    "b200_build_digest": (C.c_char_p, []),
     "b200_last_error": (C.c_char_p, []),
     "b200_launch_count": (C.c_uint64, []),
     "b200_device_supported": (_i32, []),

@@ -16,7 +16,7 @@ try:  # pragma: no cover - only when the reference is importable
     from minisgl.attention import SUPPORTED_ATTENTION_BACKENDS
 
     IN_MINISGL = True
-except Exception:
+except ImportError:
     from ..utils import Registry
 
     SUPPORTED_ATTENTION_BACKENDS = Registry("Attention Backend")

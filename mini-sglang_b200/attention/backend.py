@@ -131,6 +131,7 @@ class B200AttnBackend(BaseAttnBackend):
         self.max_graph_bs = 0
         self._workspace: Optional[torch.Tensor] = None
         self._workspace_bs = 0
+        self._retired_workspaces: List[torch.Tensor] = []
         self._lib = None
         self._sm_count = 0
         if torch.device(self.device).type == "cuda":
@@ -139,11 +140,19 @@ class B200AttnBackend(BaseAttnBackend):
 
     # ------------------------------------------------------------------ workspace
     def _get_workspace(self, bs: int) -> torch.Tensor:
+        """Split-KV workspace (fp32 partials + arrival counters) of the decode kernel.  Sized ONCE for
+        the largest batch the engine can ever hand over -- ``page_table.shape[0]`` rows =
+        ``max_running_req + 1`` (engine/engine.py:69-73) -- because captured decode graphs bake its
+        address in (partials and the counters at its tail).  Should a larger batch ever show up, a new
+        buffer is used for eager launches from then on and the old ones are kept alive, so a captured
+        graph never writes into freed memory."""
         if self._workspace is None or bs > self._workspace_bs:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("attention workspace must be sized before graph capture")
-            want = max(bs, self.max_graph_bs, 256)
+            want = max(bs, self.max_graph_bs, int(get_global_ctx().page_table.shape[0]))
             nbytes = self._lib.b200_attn_workspace_bytes(want, self.qo_head_local, self.head_dim)
+            if self._workspace is not None:
+                self._retired_workspaces.append(self._workspace)
             # zero-filled once: holds the split-KV arrival counters (left at zero by every launch)
             self._workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
             self._workspace_bs = want
@@ -225,7 +234,6 @@ class B200AttnBackend(BaseAttnBackend):
             raise RuntimeError(f"unsupported / mismatched dtypes q={q.dtype} pool={kc.dtype}")
         out = torch.empty((nnz, hq, d), dtype=q.dtype, device=q.device)
         num_slots = kc.numel() // (hkv * d)
-        ws = self._get_workspace(md.bs)
         stream = torch.cuda.current_stream(q.device).cuda_stream
         out_loc = batch.out_loc
         if out_loc.dtype != torch.int32 or not out_loc.is_contiguous():
@@ -233,6 +241,7 @@ class B200AttnBackend(BaseAttnBackend):
         if md.max_seqlen_q == 1:
             if nnz != md.bs:
                 raise RuntimeError(f"decode expects one query row per request ({nnz} vs {md.bs})")
+            ws = self._get_workspace(md.bs)
             _cabi.check(
                 self._lib.b200_attn_decode(
                     q3.data_ptr(), q3.stride(0), k2.data_ptr(), k2.stride(0), v2.data_ptr(),
@@ -254,7 +263,7 @@ class B200AttnBackend(BaseAttnBackend):
                     md.cu_seqlens_q.data_ptr(),
                     md.prefill_plan.data_ptr() if md.prefill_plan is not None else None,
                     md.bs, nnz, md.max_seqlen_q, hq, hkv, d, self.scale,
-                    out.data_ptr(), ws.data_ptr(), ws.numel(), dtype, stream,
+                    out.data_ptr(), None, 0, dtype, stream,
                 ),
                 "b200_attn_prefill",
             )

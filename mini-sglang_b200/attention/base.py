@@ -17,7 +17,7 @@ try:  # pragma: no cover - only when the reference is on sys.path
     from minisgl.attention.base import BaseAttnBackend, BaseAttnMetadata, HybridBackend
 
     USING_REFERENCE_ABCS = True
-except Exception:
+except ImportError:
     USING_REFERENCE_ABCS = False
 
     class BaseAttnMetadata(abc.ABC):

@@ -17,7 +17,6 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 INCLUDE = PKG_DIR.parent / "include"
 LIB_PATH = PKG_DIR / "libb200attn.so"
-STAMP = PKG_DIR / ".libb200attn.stamp"
 
 SOURCES = [
     "capi.cu",
@@ -61,14 +60,29 @@ def _digest(sources: List[Path]) -> str:
     return h.hexdigest()
 
 
+def built_digest() -> str:
+    """Digest the existing libb200attn.so carries ("B200DIGEST:<sha256>", also returned by
+    ``b200_build_digest()``), "" if there is no library or it predates the marker.  The digest lives
+    inside the binary, so a stale .so can never be mistaken for a current one (no side-car stamp
+    file); it is read from the file bytes because dlopen-ing the old library here would pin it for
+    the rest of the process."""
+    if not LIB_PATH.exists():
+        return ""
+    import re
+
+    m = re.search(rb"B200DIGEST:([0-9a-f]{64})", LIB_PATH.read_bytes())
+    return m.group(1).decode() if m else ""
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every .cu under csrc/ into libb200attn.so (skips when sources are unchanged)."""
+    """Compile every .cu under csrc/ into libb200attn.so (skips when the library reports the digest
+    of the current sources + flags)."""
     srcs = [CSRC / s for s in SOURCES]
     for s in srcs:
         if not s.exists():
             raise FileNotFoundError(s)
     digest = _digest(srcs)
-    if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text() == digest:
+    if not force and built_digest() == digest:
         return LIB_PATH
     objs = []
     procs = []
@@ -77,6 +91,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for s in srcs:
         o = build_dir / (s.stem + ".o")
         cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(INCLUDE), "-I", str(CSRC), "-c", str(s), "-o", str(o)]
+        if s.name == "capi.cu":
+            cmd.insert(1, f'-DB200_BUILD_DIGEST="B200DIGEST:{digest}"')
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
@@ -107,7 +123,6 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout.decode(errors="replace"))
-    STAMP.write_text(digest)
     return LIB_PATH
 
 

@@ -337,8 +337,11 @@ using namespace b200;
 
 extern "C" size_t b200_attn_workspace_bytes(int max_bs, int hq, int head_dim) {
   const size_t items = (size_t)max_bs * kMaxSplits * hq;
-  // partial o | partial (m, l) | arrival counters [max_bs][hq] (zero between launches)
-  return items * head_dim * sizeof(float) + items * 2 * sizeof(float) + (size_t)max_bs * hq * sizeof(int) + 256;
+  // partial o | partial (m, l) | (both regions rounded up to 256 B) arrival counters [max_bs][hq]
+  // (zero between launches) at the end, so the counters can never overlap the last partials
+  const size_t partials = items * head_dim * sizeof(float) + items * 2 * sizeof(float);
+  const size_t counters = (size_t)max_bs * hq * sizeof(int);
+  return (partials + 255) / 256 * 256 + (counters + 255) / 256 * 256 + 256;
 }
 
 namespace b200 {

@@ -38,7 +38,13 @@ std::atomic<int> g_decode_fused_combine{2};
 std::atomic<int> g_decode_defer{1};  // unit epilogue deferred behind the next unit's first tile
 }
 
-extern "C" int b200_abi_version(void) { return 6; }
+extern "C" int b200_abi_version(void) { return 7; }
+
+#ifndef B200_BUILD_DIGEST
+#define B200_BUILD_DIGEST "B200DIGEST:unknown"
+#endif
+// the marker prefix lets build.py find the digest in the file without loading the library
+extern "C" const char* b200_build_digest(void) { return B200_BUILD_DIGEST + 11; }
 
 extern "C" int b200_set_option(const char* name, int value) {
   if (name != nullptr && std::strcmp(name, "use_pdl") == 0) return b200::g_use_pdl.exchange(value);

@@ -214,6 +214,38 @@ def patch_minisgl_layers(model: Any) -> int:
     return count
 
 
+_FLASHINFER_SAVED: Dict[str, Callable] = {}
+
+
+def patch_flashinfer_entry_points() -> int:
+    """Point ``flashinfer.rmsnorm`` / ``fused_add_rmsnorm`` / ``apply_rope_with_cos_sin_cache_inplace``
+    at the sm_100a ops.  The reference's layers import these names from the ``flashinfer`` package
+    inside ``__init__`` (layers/norm.py:10,25, layers/rotary.py:35), so calling this BEFORE the model is
+    built (``LLM(...)`` / ``Engine(...)``) makes every norm / rotary layer bind our kernels -- including
+    inside the decode CUDA graphs, which are captured during ``Engine.__init__`` (engine/engine.py:100,
+    engine/graph.py:105-141; re-binding layer attributes afterwards only affects eager forwards).
+    Returns the number of re-bound names; :func:`restore_flashinfer_entry_points` undoes it."""
+    import flashinfer
+
+    table = {
+        "rmsnorm": ops.rmsnorm,
+        "fused_add_rmsnorm": ops.fused_add_rmsnorm,
+        "apply_rope_with_cos_sin_cache_inplace": ops.apply_rope_with_cos_sin_cache_inplace,
+    }
+    for name, fn in table.items():
+        _FLASHINFER_SAVED.setdefault(name, getattr(flashinfer, name))
+        setattr(flashinfer, name, fn)
+    return len(table)
+
+
+def restore_flashinfer_entry_points() -> None:
+    import flashinfer
+
+    for name, fn in _FLASHINFER_SAVED.items():
+        setattr(flashinfer, name, fn)
+    _FLASHINFER_SAVED.clear()
+
+
 def patch_minisgl_kernels() -> bool:
     """Point ``minisgl.kernel.indexing`` at the sm_100a row gather.  ``VocabParallelEmbedding.forward``
     imports the function from ``minisgl.kernel`` at call time (reference layers/embedding.py:32-34),
@@ -221,7 +253,7 @@ def patch_minisgl_kernels() -> bool:
     reference package is not importable (nothing to patch)."""
     try:
         import minisgl.kernel as ref_kernel
-    except Exception:
+    except ImportError:
         return False
     ref_kernel.indexing = ops.indexing
     return True

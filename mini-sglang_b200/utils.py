@@ -46,12 +46,13 @@ def set_tp_info(rank: int, size: int) -> None:
 def get_tp_info() -> TPInfo:
     """The reference's TP info when running inside mini-sglang, else the local one."""
     try:  # pragma: no cover - only inside a real mini-sglang process
-        from minisgl.distributed import get_tp_info as _ref
-
-        info = _ref()
-        return TPInfo(info.rank, info.size)
-    except Exception:
+        from minisgl.distributed import try_get_tp_info as _ref
+    except ImportError:  # reference not installed: the stand-alone TP info set by set_tp_info()
         return _TP
+    info = _ref()  # errors of the reference propagate
+    if info is None:  # reference importable but no engine running in this process (tests, bench.py)
+        return _TP
+    return TPInfo(info.rank, info.size)
 
 
 class Registry(Generic[T]):
