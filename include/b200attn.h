@@ -195,6 +195,43 @@ B200_API int b200_attn_prefill(const void* q, int64_t q_row_stride, const void* 
                       int hkv, int head_dim, float scale, void* out, void* workspace,
                       size_t workspace_bytes, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * f4  Tensor-parallel all-reduce for decode-sized messages, optionally fused with the residual add +
+ *     RMSNorm that consumes it.  Replaces PyNCCLCommunicator.all_reduce (M/kernel/pynccl.py:14-22 ->
+ *     M/kernel/csrc/src/pynccl.cu:93-134: copy into the symmetric window, ncclAllReduce, copy back)
+ *     behind the reference's communication plug-in point DistributedCommunicator.plugins
+ *     (M/distributed/impl.py:60-97), called after o_proj / down_proj (M/layers/linear.py:102-106,
+ *     122-126), and -- fused form -- the flashinfer.fused_add_rmsnorm that follows
+ *     (M/layers/norm.py:32-38).  One-shot "push" algorithm over NVLink peer memory: see
+ *     csrc/allreduce.cu.  Every rank must issue the same sequence of calls with the same shapes.
+ *
+ *     Set-up (host, once): each rank allocates a region of b200_ar_region_bytes(world, max_bytes)
+ *     with b200_ar_alloc (zero-filled), exports it with b200_ar_ipc_handle (64 opaque bytes), the
+ *     handles are exchanged by the caller (torch.distributed), peers are mapped with b200_ar_ipc_open,
+ *     and b200_ar_create receives the `world` base pointers in rank order (bases[rank] = own region;
+ *     opened_mask[i] != 0 marks pointers b200_ar_destroy must unmap).
+ *
+ *     b200_ar_allreduce: x [rows, dim] (row stride in elements), 16-bit floats, rows*dim*2 <= max_bytes.
+ *       residual == weight == NULL:  out <- sum over ranks of x (fp32 accumulation in rank order, one
+ *         rounding; identical bits on every rank); out may alias x.
+ *       else:  y = that sum; residual <- round(y + residual); out <- round((y + residual) *
+ *         rsqrt(mean((y + residual)^2) + eps) * weight)  == b200_fused_add_rmsnorm(y, residual, ...),
+ *         bit for bit; out may alias x.
+ *     Capturable in CUDA graphs (the launch epoch lives in device memory); never synchronises.
+ * ------------------------------------------------------------------------------------- */
+B200_API size_t b200_ar_region_bytes(int world, size_t max_bytes);
+B200_API int b200_ar_alloc(size_t bytes, void** ptr);
+B200_API int b200_ar_ipc_handle(void* ptr, void* handle64);
+B200_API int b200_ar_ipc_open(const void* handle64, void** ptr);
+B200_API int b200_ar_create(int rank, int world, void* const* bases, const int* opened_mask,
+                            size_t max_bytes, void** comm);
+B200_API int b200_ar_destroy(void* comm, int free_local);
+B200_API size_t b200_ar_max_bytes(const void* comm);
+B200_API int b200_ar_allreduce(void* comm, const void* x, int64_t x_row_stride, void* out,
+                               int64_t out_row_stride, void* residual, int64_t res_row_stride,
+                               const void* weight, int64_t rows, int dim, float eps, int dtype,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

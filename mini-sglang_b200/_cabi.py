@@ -58,6 +58,14 @@ SIGNATURES = {
         [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp]
         + [_i32, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _i32, _vp],
     ),
+    "b200_ar_region_bytes": (_sz, [_i32, _sz]),
+    "b200_ar_alloc": (_i32, [_sz, C.POINTER(_vp)]),
+    "b200_ar_ipc_handle": (_i32, [_vp, _vp]),
+    "b200_ar_ipc_open": (_i32, [_vp, C.POINTER(_vp)]),
+    "b200_ar_create": (_i32, [_i32, _i32, C.POINTER(_vp), C.POINTER(_i32), _sz, C.POINTER(_vp)]),
+    "b200_ar_destroy": (_i32, [_vp, _i32]),
+    "b200_ar_max_bytes": (_sz, [_vp]),
+    "b200_ar_allreduce": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _f32, _i32, _vp]),
 }
 
 

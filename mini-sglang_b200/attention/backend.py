@@ -132,6 +132,10 @@ class B200AttnBackend(BaseAttnBackend):
         self._workspace: Optional[torch.Tensor] = None
         self._workspace_bs = 0
         self._retired_workspaces: List[torch.Tensor] = []
+        # pinned staging ring for the per-batch (table_idx, cached_len, device_len) triples: re-used, never
+        # re-allocated per step; an entry is rewritten only after the copy that read it has completed
+        self._info_ring: List[Tuple[torch.Tensor, "torch.cuda.Event"]] = []
+        self._info_next = 0
         self._lib = None
         self._sm_count = 0
         if torch.device(self.device).type == "cuda":
@@ -159,6 +163,29 @@ class B200AttnBackend(BaseAttnBackend):
         return self._workspace
 
     # ------------------------------------------------------------------ metadata
+    _INFO_RING = 4  # > the scheduler's look-ahead of one batch (overlap scheduling, scheduler.py:83-106)
+
+    def _upload_req_info(self, flat: List[int]) -> torch.Tensor:
+        """Host -> device copy of the request triples through a small ring of pinned buffers (the
+        reference allocates a fresh pinned tensor per step, fa.py:76-90 ``pin_memory=True``)."""
+        n = len(flat)
+        if len(self._info_ring) < self._INFO_RING:
+            cap = max(3 * int(get_global_ctx().page_table.shape[0]), n)
+            host = torch.empty(cap, dtype=torch.int32, pin_memory=True)
+            self._info_ring.append((host, torch.cuda.Event()))
+            slot = len(self._info_ring) - 1
+        else:
+            slot = self._info_next
+            self._info_next = (slot + 1) % self._INFO_RING
+            self._info_ring[slot][1].synchronize()  # the copy issued 4 batches ago: long done
+            if self._info_ring[slot][0].numel() < n:
+                self._info_ring[slot] = (torch.empty(n, dtype=torch.int32, pin_memory=True), self._info_ring[slot][1])
+        host, ev = self._info_ring[slot]
+        host[:n] = torch.tensor(flat, dtype=torch.int32)
+        dev_info = host[:n].to(self.device, non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return dev_info
+
     def prepare_metadata(self, batch) -> None:
         reqs = batch.padded_reqs
         bs = len(reqs)
@@ -166,9 +193,7 @@ class B200AttnBackend(BaseAttnBackend):
         if self._lib is None:
             raise RuntimeError("B200AttnBackend.prepare_metadata needs a CUDA device (no CPU path)")
         dev = self.device
-        info = torch.tensor(flat, dtype=torch.int32, device="cpu", pin_memory=True).to(
-            dev, non_blocking=True
-        )
+        info = self._upload_req_info(flat)
         off_seq, off_cuq, off_cuk, off_plan, total = small_block_layout(bs)
         small = torch.empty(total, dtype=torch.int32, device=dev)
         page_table = get_global_ctx().page_table

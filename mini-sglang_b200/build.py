@@ -28,6 +28,7 @@ SOURCES = [
     "tma_host.cu",
     "attn_prefill.cu",
     "attn_prefill_tc.cu",
+    "allreduce.cu",
 ]
 
 NVCC_FLAGS = [

@@ -249,12 +249,14 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(
   unpack8<T>(xv, f);
   if constexpr (kNorm) {
     const T* w = is_q ? qw : kw;
+    // the group reduction runs unconditionally: q-head and k-head groups share a warp, so a
+    // full-mask shuffle must not sit behind the per-group `w != nullptr` branch
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if (w != nullptr) {  // uniform per group
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
-#pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
       const float rcp = rsqrtf(ss / (float)kDim + eps);
       float wf[8];
       Vec8 wv = *reinterpret_cast<const Vec8*>(w + j * 8);

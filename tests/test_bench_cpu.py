@@ -37,13 +37,24 @@ def test_live_sets_shrink_and_lengths_grow():
 
 
 def test_prefill_batches_respect_the_token_budget():
-    s = bench.Schedule()
-    batches = s.prefill_batches()
-    assert sum(len(b) for b in batches) == 256
-    assert [t for b in batches for (t, _, _) in b] == list(range(256))
-    for b in batches:
-        assert sum(d for (_, _, d) in b) <= bench.MAX_EXTEND_TOKENS
-        assert all(c == 0 and d == s.in_lens[t] for (t, c, d) in b)
+    """Greedy admission with chunk splitting (reference scheduler/prefill.py:64-90): every batch spends at
+    most max_extend_tokens, a prompt straddling the budget continues as a cached_len > 0 chunk in the
+    next batch, and the chunks of a request tile [0, in_len) exactly."""
+    for name in ("cfg1", "cfg2", "cfg4"):
+        wl = bench.WORKLOADS[name]
+        s = bench.Schedule(wl)
+        batches = s.prefill_batches()
+        covered = {}
+        for b in batches:
+            assert 0 < sum(d - c for (_, c, d) in b) <= wl.max_extend
+            for (t, c, d) in b:
+                start = min(wl.shared_prefix, (s.in_lens[t] - 1) // 64 * 64) if wl.shared_prefix else 0
+                assert c == covered.get(t, start) and c < d <= s.in_lens[t]
+                covered[t] = d
+        assert covered == {t: n for t, n in enumerate(s.in_lens)}
+        assert [len(b) for b in batches[:-1]] and all(sum(d - c for (_, c, d) in b) == wl.max_extend for b in batches[:-1])
+    s = bench.Schedule(bench.WORKLOADS["cfg4"])
+    assert s.sum_kv == 68935680 and s.n_iters == 255  # BASELINE.md section 3, cfg4
 
 
 def test_algorithmic_work_formulas():
@@ -74,10 +85,13 @@ def test_graph_batch_sizes_match_the_reference_engine():
 
 def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--ref-layers", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--ref-reqs", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # nothing extrapolated: the reported step time is the measured one, tokens = requests actually attended
+    assert abs(d["value"] - 1 / (d["ms_per_step"] * 1e-3)) / d["value"] < 0.02
+    assert d["config"]["page_size"] == 64 and d["config"]["layers"] == 28 and "ALL 28 layers" in d["config"]["sample"]

@@ -215,6 +215,29 @@ def test_fused_qknorm_rope_equals_three_launches(b200, native_lib, with_norm):
     assert torch.equal(a.view(torch.int16), b.view(torch.int16))
 
 
+@pytest.mark.parametrize("which", ["q_only", "k_only"])
+@pytest.mark.parametrize("d", [64, 128])
+def test_fused_qknorm_rope_mixed_weights(b200, native_lib, which, d):
+    """Only one of q_weight / k_weight given: a warp then holds normed and un-normed head groups side
+    by side (2 groups per warp at D=128, 4 at D=64) -- the group reduction must not diverge."""
+    torch.manual_seed(6)
+    nnz, hq, hkv = 37, 3, 1  # odd head counts: q and k groups share warps
+    cache = o_rope.ref_cos_sin_cache(d, 512, 1e6).cuda()
+    qkv = torch.randn(nnz, (hq + 2 * hkv) * d).to(torch.bfloat16).cuda()
+    pos = torch.randint(0, 512, (nnz,), dtype=torch.int32).cuda()
+    qw = (torch.rand(d) + 0.5).to(torch.bfloat16).cuda() if which == "q_only" else None
+    kw = (torch.rand(d) + 0.5).to(torch.bfloat16).cuda() if which == "k_only" else None
+    a, b = qkv.clone(), qkv.clone()
+    qa, ka = a[:, : hq * d], a[:, hq * d : (hq + hkv) * d]
+    if qw is not None:
+        b200.ops.rmsnorm(qa.view(nnz, hq, d), qw, 1e-6, out=qa.view(nnz, hq, d))
+    if kw is not None:
+        b200.ops.rmsnorm(ka.view(nnz, hkv, d), kw, 1e-6, out=ka.view(nnz, hkv, d))
+    b200.ops.apply_rope_with_cos_sin_cache_inplace(pos, qa, ka, d, cache)
+    b200.ops.qknorm_rope_inplace(pos, b[:, : hq * d], b[:, hq * d : (hq + hkv) * d], d, cache, qw, kw, 1e-6)
+    assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+
 # ------------------------------------------------------------------ against FlashInfer itself
 def _fi():
     import numpy as np

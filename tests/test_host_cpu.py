@@ -38,6 +38,44 @@ def test_abi_version_and_helpers(b200, native_lib):
         b200._cabi.set_option("no_such_option", 1)
 
 
+def test_workspace_counters_never_overlap_partials(native_lib):
+    """with odd bs*hq the arrival counters (placed at floor256(size) - ceil256(bs*hq*4) by
+    b200_attn_decode) used to overlap the last (m, l) partials.  Both regions are now 256-aligned."""
+    for bs, hq in [(257, 7), (1, 1), (3, 5), (255, 3), (256, 16), (129, 9)]:
+        total = native_lib.b200_attn_workspace_bytes(bs, hq, 128)
+        items = bs * 16 * hq
+        partials_end = items * 128 * 4 + items * 2 * 4
+        counters_start = total // 256 * 256 - (bs * hq * 4 + 255) // 256 * 256
+        assert counters_start >= partials_end, (bs, hq, counters_start, partials_end)
+
+
+def test_build_digest_is_embedded(b200, native_lib):
+    from importlib import import_module
+
+    build = import_module("mini-sglang_b200.build")
+    assert native_lib.b200_build_digest().decode() == build.built_digest() != ""
+
+
+def test_allreduce_host_api_validates(b200, native_lib):
+    """Set-up half of the all-reduce ABI needs no GPU: region sizing and communicator creation."""
+    assert native_lib.b200_ar_region_bytes(8, 1 << 20) >= 2 * 8 * (1 << 20) + 8 * 128 * 4
+    bases = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    opened = (ctypes.c_int * 2)(0, 0)
+    comm = ctypes.c_void_p()
+    assert native_lib.b200_ar_create(0, 2, bases, opened, 1000, ctypes.byref(comm)) == 0
+    assert native_lib.b200_ar_max_bytes(comm) == 1024  # rounded up to 256
+    # message larger than the slot, NULL communicator, residual without weight: rejected before any launch
+    buf = (ctypes.c_char * 64)()
+    p = ctypes.addressof(buf) // 16 * 16
+    assert native_lib.b200_ar_allreduce(comm, p, 1024, p, 1024, None, 0, None, 4, 1024, 0.0, 0, None) != 0
+    assert b"exceeds" in native_lib.b200_last_error()
+    assert native_lib.b200_ar_allreduce(None, p, 8, p, 8, None, 0, None, 1, 8, 0.0, 0, None) != 0
+    assert native_lib.b200_ar_allreduce(comm, p, 8, p, 8, p, 8, None, 1, 8, 0.0, 0, None) != 0
+    assert native_lib.b200_ar_destroy(comm, 0) == 0
+    assert native_lib.b200_ar_create(2, 2, bases, opened, 1000, ctypes.byref(comm)) != 0
+    assert native_lib.b200_ar_create(0, 9, bases, opened, 1000, ctypes.byref(comm)) != 0
+
+
 def test_argument_validation_returns_error_not_crash(b200, native_lib):
     """Bad arguments are rejected before any CUDA call (mirrors TensorMatcher -> RuntimeError)."""
     buf = (ctypes.c_char * 64)()

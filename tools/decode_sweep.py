@@ -54,7 +54,7 @@ def main():
             bs = batch.padded_size
             pos_h, loc_h = r.host_inputs(batch)
             batch.positions, batch.out_loc = pos_h.to(dev), loc_h.to(dev)
-            qs = [r.qkv[l, :bs].split([hq * D, hkv * D, hkv * D], dim=-1) for l in range(args.layers)]
+            qs = [r.qkv_views(l, bs) for l in range(args.layers)]
             nbytes = bench.decode_bytes_per_layer([(x.table_idx, x.cached_len, x.device_len) for x in batch.padded_reqs], hq, hkv)
             best = None
             extra_sets = [dict(kv.split("=") for kv in es.split(",") if kv) for es in args.opts.split(";")] if args.opts else [{}]

@@ -82,7 +82,7 @@ def main():
         batch.positions, batch.out_loc = pos_h.to(dev), loc_h.to(dev)
         r.backend.prepare_metadata(batch)
         md = batch.attn_metadata
-        qs = [r.qkv[l, :bs].split([hq * D, hkv * D, hkv * D], dim=-1) for l in range(L)]
+        qs = [r.qkv_views(l, bs) for l in range(L)]
         nbytes = bench.decode_bytes_per_layer(tr, hq, hkv)
 
         def ours_decode():

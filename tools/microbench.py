@@ -4,6 +4,8 @@ used under ncu for the per-kernel captures in profiles/ and stand-alone for quic
 
     python tools/microbench.py decode --iter 500 --layers 4 --reps 5
     python tools/microbench.py prefill --layers 2
+    python tools/microbench.py prefill --config cfg4 --layers 4            # 2 x 4096-token prompts, GQA 8
+    python tools/microbench.py prefill --lens 0:8192 --hq 8 --hkv 1        # custom (cached:total,...) prompts
 """
 import argparse
 import importlib
@@ -25,12 +27,18 @@ def main():
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--page-size", type=int, default=64)
-    ap.add_argument("--hq", type=int, default=bench.HQ)
-    ap.add_argument("--hkv", type=int, default=bench.HKV)
+    ap.add_argument("--config", default="cfg1", choices=sorted(bench.WORKLOADS))
+    ap.add_argument("--hq", type=int, default=0, help="override the (local) q heads of the config")
+    ap.add_argument("--hkv", type=int, default=0)
+    ap.add_argument("--lens", default="", help="prefill: comma list of cached:total prompt lengths instead of the schedule's batches")
+    ap.add_argument("--batches", type=int, default=2)
     ap.add_argument("--opt", action="append", default=[], help="name=value for b200_set_option")
     args = ap.parse_args()
+    bench.set_workload(args.config)
     bench.L = args.layers
-    bench.HQ, bench.HKV = args.hq, args.hkv
+    if args.hq:
+        bench.HQ, bench.HKV = args.hq, args.hkv or bench.HKV
+    args.hq, args.hkv = bench.HQ, bench.HKV
     pkg = importlib.import_module("mini-sglang_b200")
     pkg.build_native()
     for o in args.opt:
@@ -50,7 +58,7 @@ def main():
             pos_h, loc_h = r.host_inputs(batch)
             batch.positions, batch.out_loc = pos_h.to(dev), loc_h.to(dev)
             r.backend.prepare_metadata(batch)
-            qs = [r.qkv[l, :bs].split([hq * D, hkv * D, hkv * D], dim=-1) for l in range(args.layers)]
+            qs = [r.qkv_views(l, bs) for l in range(args.layers)]
             nbytes = bench.decode_bytes_per_layer([(x.table_idx, x.cached_len, x.device_len) for x in batch.padded_reqs], hq, hkv)
             times = []
             for rep in range(args.reps):
@@ -76,7 +84,10 @@ def main():
                     eb = bs * (hq + hkv) * D * 2 * 2
                     print(f"qknorm_rope bs={bs}: {us:.1f} us/layer, {eb / us / 1e3:.0f} GB/s")
         else:
-            for tr in sched.prefill_batches()[:2]:
+            batches = sched.prefill_batches()[: args.batches]
+            if args.lens:
+                batches = [[(i, int(x.split(":")[0]), int(x.split(":")[1])) for i, x in enumerate(args.lens.split(","))]]
+            for tr in batches:
                 batch = r.make_batch(tr, "prefill")
                 pos_h, loc_h = r.host_inputs(batch)
                 nnz = pos_h.numel()
