@@ -1,8 +1,8 @@
 """In-situ drop-in test (VERDICT r1, row b'): the UNMODIFIED reference -- `minisgl.llm.LLM` ->
 `Scheduler` -> `Engine` -> `GraphRunner` -> `CacheManager` / radix cache, pip-installed into the
-git-ignored baseline/_ref -- drives `--attn b200` and, in separate processes, its own `fi` and
+git-ignored oracle/_ref/minisgl_site -- drives `--attn b200` and, in separate processes, its own `fi` and
 `trtllm` backends on the same requests (Qwen3-0.6B shape, dummy weights, greedy, teacher-forced),
-see tools/insitu.py.  Skipped when baseline/_ref is absent (the reference cannot travel in git).
+see tools/insitu.py.  Skipped when that directory is absent (the reference cannot travel in git).
 
 Gates:
   * structure: chunked prefill, radix-hit extends and padded CUDA-graph replays all happened, through
@@ -36,7 +36,7 @@ LOGITS_TOL = 1e-3
 @pytest.fixture(scope="module")
 def summary():
     if not insitu.reference_available():
-        pytest.skip("baseline/_ref/minisgl not installed (pip install --no-deps --target baseline/_ref <reference>)")
+        pytest.skip("reference not installed (pip install --no-deps --target oracle/_ref/minisgl_site <reference>)")
     import argparse
 
     out = ROOT / "gpurun_out" / "insitu_summary.json"

@@ -158,8 +158,9 @@ def main() -> None:
     res["checks"]["stress_1500_calls"] = bool(ok_stress)
 
     # ---------------------------------------------------------------- 5. reference plug-in point
-    ref = ROOT / "baseline" / "_ref"
-    if (ref / "minisgl").exists():
+    ref = next((d for d in (ROOT / "oracle" / "_ref" / "minisgl_site", ROOT / "baseline" / "_ref")
+                if (d / "minisgl" / "core.py").exists()), None)
+    if ref is not None:
         sys.path.insert(0, str(ref))
         from minisgl.distributed import DistributedCommunicator
 

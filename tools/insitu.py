@@ -37,7 +37,10 @@ import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-REF = ROOT / "baseline" / "_ref"
+# the unmodified reference, pip-installed (--no-deps --target) into a git-ignored directory that travels to
+# the GPU box with the snapshot: oracle/_ref/minisgl_site (preferred) or baseline/_ref
+REF = next((d for d in (ROOT / "oracle" / "_ref" / "minisgl_site", ROOT / "baseline" / "_ref")
+            if (d / "minisgl" / "core.py").exists()), ROOT / "oracle" / "_ref" / "minisgl_site")
 
 QWEN3_0_6B = {  # public HF config of Qwen/Qwen3-0.6B
     "architectures": ["Qwen3ForCausalLM"], "model_type": "qwen3", "hidden_size": 1024,
@@ -50,7 +53,7 @@ QWEN3_0_6B = {  # public HF config of Qwen/Qwen3-0.6B
 
 
 def reference_available() -> bool:
-    return (REF / "minisgl" / "__init__.py").exists()
+    return (REF / "minisgl" / "core.py").exists()
 
 
 def workload():
@@ -339,7 +342,7 @@ def main() -> None:
     r.add_argument("--layers", type=int, default=28)
     args = ap.parse_args()
     if not reference_available():
-        raise SystemExit("baseline/_ref/minisgl is missing: pip install --no-deps --target baseline/_ref <reference>")
+        raise SystemExit("the reference is not installed: python -m pip install --no-index --no-build-isolation --no-deps --target oracle/_ref/minisgl_site <copy of the reference>")
     child(args) if args.mode == "child" else run(args)
 
 
