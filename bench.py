@@ -395,8 +395,12 @@ class AttentionPathRunner:
     # ---- one layer of the hot path on rows [0, n) of the static buffers
     def layer(self, l: int, n: int, batch) -> None:
         q, k, v = self.qkv_views(l, n)
-        self.pkg.ops.qknorm_rope_inplace(batch.positions, q, k, D, self.rotary._cos_sin_cache, self.qw, self.kw, EPS)
-        o = self.backend.forward(q.view(n, self.hq, D), k, v, l, batch)
+        if self.fuse_pre_attention:  # qk-norm + RoPE + append + attention: one launch
+            o = self.backend.forward_decode_fused(q.view(n, self.hq, D), k, v, l, batch, batch.positions,
+                                                  self.rotary._cos_sin_cache, self.qw, self.kw, EPS)
+        else:
+            self.pkg.ops.qknorm_rope_inplace(batch.positions, q, k, D, self.rotary._cos_sin_cache, self.qw, self.kw, EPS)
+            o = self.backend.forward(q.view(n, self.hq, D), k, v, l, batch)
         self._last_out = o
         if self.ar is not None:
             self.ar.all_reduce(self.hidden[:n], out=self.hidden_out[:n], residual=self.resid[:n],
@@ -660,7 +664,8 @@ def run_ours(args) -> dict:
     g_hq, g_hkv = wl.hq // shard, max(1, wl.hkv // shard)
     hq, hkv = g_hq // world, max(1, g_hkv // world)
     sched = Schedule(wl)
-    runner = AttentionPathRunner(pkg, sched, g_hq, g_hkv, args.page_size, dev, world, tp_group, args.allreduce)
+    runner = AttentionPathRunner(pkg, sched, g_hq, g_hkv, args.page_size, dev, world, tp_group, args.allreduce,
+                                 fuse_pre_attention=not args.unfused_pre_attention)
     lib = runner.lib
     peaks = load_peaks()
 
@@ -861,6 +866,8 @@ def run_ours(args) -> dict:
                                f"decode iterations sampled evenly over {sched.n_iters}",
                    "layers": L, "hq": wl.hq, "hkv": wl.hkv, "hq_local": hq, "hkv_local": hkv, "head_dim": D,
                    "page_size": args.page_size, "parallelism": par, "cuda_graph": True,
+                   "decode_step": ("per layer ONE launch: qk-norm + RoPE + KV append + attention (b200_attn_decode_fused)"
+                                   if runner.fuse_pre_attention else "per layer: qk-norm+RoPE launch, attention(+append) launch"),
                    "allreduce": {"b200": "captured: one-shot NVLink push all-reduce of [bs,%d] bf16 fused with residual add + RMSNorm "
                                          "(csrc/allreduce.cu), one launch per layer inside the decode graph" % HIDDEN,
                                  "nccl": "nccl all-reduce [bs,%d] bf16 x %d per step (eager, behind the graph replay)" % (HIDDEN, L),
@@ -1023,6 +1030,8 @@ def main() -> None:
     ap.add_argument("--prefill-batches", type=int, default=0, help="time only the first N prompt batches (0 = all)")
     ap.add_argument("--prefill-layers", type=int, default=0, help="time only N layers per prompt batch (0 = all)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--unfused-pre-attention", action="store_true",
+                    help="decode step = qk-norm+RoPE launch, then attention (round-1 chain) instead of the single fused launch")
     ap.add_argument("--skip-ref-gpu", action="store_true")
     ap.add_argument("--no-allreduce", action="store_true")
     ap.add_argument("--allreduce", default="b200", choices=["b200", "nccl"], help="TP all-reduce implementation (N > 1)")

@@ -47,6 +47,8 @@ B200_API int b200_device_supported(void);
 /* Kernel selection knobs (debug / cross-checking only; defaults are the product path):
  *   "decode_impl": 1 = tcgen05 + TMA kernel (default), 0 = cp.async / CUDA-core kernel.
  *   "prefill_impl": 1 = tcgen05 kernel (default, needs prefill_plan), 0 = mma.sync bring-up kernel.
+ *   "prefill_full_row": 1 (default) = tcgen05 prefill with one softmax thread per query row (8 warps, whole score
+ *       row in registers); 0 = two threads per row (16 warps), the round-1 variant.
  *   "decode_lookahead": S^T buffers the UMMA issuer may run ahead (2..4, default 4).
  *   "decode_fused_combine": 0 = separate combine launch, 1 = merge split-KV partials inside the decode
  *       launch, 2 = auto (default): in-kernel, and no combine launch, exactly when the plan policy
@@ -180,6 +182,21 @@ B200_API int b200_attn_decode(const void* q, int64_t q_row_stride, const void* k
                      const int32_t* seq_lens, const int32_t* decode_plan, int bs, int hq, int hkv,
                      int head_dim, float scale, void* out, void* workspace, size_t workspace_bytes,
                      int dtype, void* stream);
+
+/* Decode with the pre-attention sequence of AttentionLayer.forward (M/layers/attention.py:50-54: per-head
+ * q-norm, k-norm, neox RoPE -- three launches in the reference) folded into the same launch: q and k are the
+ * RAW rows of the qkv projection; the kernel norms + ropes them on the fly (arithmetic of
+ * b200_qknorm_rope_inplace, bit for bit), appends the roped k row and v row at out_loc and attends.  q / k
+ * are NOT modified in memory (nothing downstream of attention reads them, M/models/utils.py:118-123).
+ * q_weight / k_weight may be NULL (models without qk-norm); positions int32 [bs]; cos_sin_cache fp32
+ * [max_pos, 128] = cos | sin (M/layers/rotary.py:24-32).  Everything else as b200_attn_decode. */
+B200_API int b200_attn_decode_fused(const void* q, int64_t q_row_stride, const void* k, int64_t k_row_stride,
+                     const void* v, int64_t v_row_stride, const void* q_weight, const void* k_weight, float eps,
+                     const int32_t* positions, const float* cos_sin_cache, void* k_cache, void* v_cache,
+                     int64_t num_slots, int page_size, const int32_t* out_loc, const int32_t* slot_table,
+                     int64_t slot_table_stride, const int32_t* seq_lens, const int32_t* decode_plan, int bs,
+                     int hq, int hkv, int head_dim, float scale, void* out, void* workspace,
+                     size_t workspace_bytes, int dtype, void* stream);
 
 /* Prefill / extend: ragged query rows, cu_seqlens_q[bs+1]; request r has
  * q_len = cu_seqlens_q[r+1]-cu_seqlens_q[r] new tokens at kv positions

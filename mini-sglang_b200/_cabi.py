@@ -53,6 +53,11 @@ SIGNATURES = {
         [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp]
         + [_i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _i32, _vp],
     ),
+    "b200_attn_decode_fused": (
+        _i32,
+        [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp]
+        + [_i32, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _i32, _vp],
+    ),
     "b200_attn_prefill": (
         _i32,
         [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp]

@@ -30,6 +30,9 @@ from ..core import get_global_ctx
 from ..utils import div_even, get_tp_info
 from .base import BaseAttnBackend, BaseAttnMetadata
 
+import os
+
+_DEBUG_CHECKS = os.environ.get("B200_DEBUG_CHECKS", "0") not in ("", "0")
 _PLAN_HEADER = 4
 _DTYPE_CODE = {torch.bfloat16: 0, torch.float16: 1}
 
@@ -237,7 +240,7 @@ class B200AttnBackend(BaseAttnBackend):
         )
 
     # ------------------------------------------------------------------ forward
-    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, layer_id: int, batch):
+    def _check_inputs(self, q, k, v, layer_id, batch):
         md = batch.attn_metadata
         if not isinstance(md, B200Metadata):
             raise RuntimeError("batch.attn_metadata was not prepared by B200AttnBackend")
@@ -257,12 +260,17 @@ class B200AttnBackend(BaseAttnBackend):
         dtype = _DTYPE_CODE.get(q.dtype)
         if dtype is None or kc.dtype != q.dtype:
             raise RuntimeError(f"unsupported / mismatched dtypes q={q.dtype} pool={kc.dtype}")
-        out = torch.empty((nnz, hq, d), dtype=q.dtype, device=q.device)
-        num_slots = kc.numel() // (hkv * d)
-        stream = torch.cuda.current_stream(q.device).cuda_stream
         out_loc = batch.out_loc
         if out_loc.dtype != torch.int32 or not out_loc.is_contiguous():
             raise RuntimeError("batch.out_loc must be a contiguous int32 vector")
+        return md, nnz, q3, k2, v2, kc, vc, dtype, out_loc
+
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, layer_id: int, batch):
+        md, nnz, q3, k2, v2, kc, vc, dtype, out_loc = self._check_inputs(q, k, v, layer_id, batch)
+        hq, hkv, d = self.qo_head_local, self.kv_head_local, self.head_dim
+        out = torch.empty((nnz, hq, d), dtype=q.dtype, device=q.device)
+        num_slots = kc.numel() // (hkv * d)
+        stream = torch.cuda.current_stream(q.device).cuda_stream
         if md.max_seqlen_q == 1:
             if nnz != md.bs:
                 raise RuntimeError(f"decode expects one query row per request ({nnz} vs {md.bs})")
@@ -279,6 +287,12 @@ class B200AttnBackend(BaseAttnBackend):
                 "b200_attn_decode",
             )
         else:
+            # Contract of the tcgen05 prefill kernel: it appends the tile that holds a unit's own tokens
+            # at slot_table[r, cached + i] (the metadata snapshot), which equals batch.out_loc by the
+            # reference's construction out_loc = page_table[table_idx, cached_len:device_len]
+            # (scheduler/scheduler.py:207-210); B200_DEBUG_CHECKS=1 verifies it per call (host sync).
+            if _DEBUG_CHECKS:
+                self._assert_out_loc_matches_slot_table(md, out_loc)
             _cabi.check(
                 self._lib.b200_attn_prefill(
                     q3.data_ptr(), q3.stride(0), k2.data_ptr(), k2.stride(0), v2.data_ptr(),
@@ -292,6 +306,50 @@ class B200AttnBackend(BaseAttnBackend):
                 ),
                 "b200_attn_prefill",
             )
+        return out
+
+    @staticmethod
+    def _assert_out_loc_matches_slot_table(md: "B200Metadata", out_loc: torch.Tensor) -> None:
+        lens = md.cache_seqlens.tolist()
+        cu_q = md.cu_seqlens_q.tolist()
+        want = torch.cat([md.page_table[i, n - (cu_q[i + 1] - cu_q[i]) : n] for i, n in enumerate(lens)])
+        if not torch.equal(want, out_loc[: want.numel()]):
+            raise RuntimeError("batch.out_loc != page_table[table_idx, cached_len:device_len] "
+                               "(the fused prefill append relies on the reference's invariant)")
+
+    def forward_decode_fused(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, layer_id: int, batch,
+                             positions: torch.Tensor, cos_sin_cache: torch.Tensor,
+                             q_weight: Optional[torch.Tensor], k_weight: Optional[torch.Tensor], eps: float):
+        """Decode forward with the pre-attention sequence of ``AttentionLayer.forward`` (reference
+        layers/attention.py:50-54: q-norm, k-norm, RoPE) folded into the attention launch: ``q`` / ``k``
+        are the RAW rows of the qkv projection and stay untouched; the pool receives the normed + roped
+        k row.  Bit-identical to ``ops.qknorm_rope_inplace`` followed by :meth:`forward`."""
+        md, nnz, q3, k2, v2, kc, vc, dtype, out_loc = self._check_inputs(q, k, v, layer_id, batch)
+        if md.max_seqlen_q != 1 or nnz != md.bs:
+            raise RuntimeError("forward_decode_fused is for decode batches (one query row per request)")
+        if positions.dtype != torch.int32 or positions.numel() != nnz or not positions.is_contiguous():
+            raise RuntimeError("forward_decode_fused: positions must be a contiguous int32 [bs] vector")
+        if cos_sin_cache.dtype != torch.float32 or cos_sin_cache.shape[-1] != self.head_dim or not cos_sin_cache.is_contiguous():
+            raise RuntimeError("forward_decode_fused: cos_sin_cache must be contiguous fp32 [max_pos, head_dim]")
+        for w in (q_weight, k_weight):
+            if w is not None and (w.dtype != q.dtype or w.shape != (self.head_dim,) or not w.is_contiguous()):
+                raise RuntimeError("forward_decode_fused: norm weights must be contiguous [head_dim] of q's dtype")
+        hq, hkv, d = self.qo_head_local, self.kv_head_local, self.head_dim
+        out = torch.empty((nnz, hq, d), dtype=q.dtype, device=q.device)
+        ws = self._get_workspace(md.bs)
+        _cabi.check(
+            self._lib.b200_attn_decode_fused(
+                q3.data_ptr(), q3.stride(0), k2.data_ptr(), k2.stride(0), v2.data_ptr(), v2.stride(0),
+                q_weight.data_ptr() if q_weight is not None else None,
+                k_weight.data_ptr() if k_weight is not None else None, float(eps),
+                positions.data_ptr(), cos_sin_cache.data_ptr(), kc.data_ptr(), vc.data_ptr(),
+                kc.numel() // (hkv * d), self.page_size, out_loc.data_ptr(), md.page_table.data_ptr(),
+                md.page_table.stride(0), md.cache_seqlens.data_ptr(), md.decode_plan.data_ptr(), md.bs, hq,
+                hkv, d, self.scale, out.data_ptr(), ws.data_ptr(), ws.numel(), dtype,
+                torch.cuda.current_stream(q.device).cuda_stream,
+            ),
+            "b200_attn_decode_fused",
+        )
         return out
 
     # ------------------------------------------------------------------ CUDA graphs

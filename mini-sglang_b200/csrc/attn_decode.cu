@@ -351,17 +351,19 @@ int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, c
                      const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
                      const int32_t* plan, int bs, int hq, int hkv, int64_t num_slots, int page_size,
                      float scale_log2, void* out, float* part_o, float* part_ml, int* counters,
-                     int dtype, cudaStream_t st);
+                     int dtype, cudaStream_t st, int fuse, const void* qw, const void* kw, float eps,
+                     const int32_t* positions, const float* cos_sin);
 }  // namespace b200
 
-extern "C" int b200_attn_decode(const void* q, int64_t q_row_stride, const void* k,
+static int attn_decode_impl(const void* q, int64_t q_row_stride, const void* k,
                                 int64_t k_row_stride, const void* v, int64_t v_row_stride,
                                 void* k_cache, void* v_cache, int64_t num_slots, int page_size,
                                 const int32_t* out_loc,
                                 const int32_t* slot_table, int64_t slot_table_stride,
                                 const int32_t* seq_lens, const int32_t* decode_plan, int bs, int hq,
                                 int hkv, int head_dim, float scale, void* out, void* workspace,
-                                size_t workspace_bytes, int dtype, void* stream) {
+                                size_t workspace_bytes, int dtype, void* stream, int fuse, const void* qw,
+                                const void* kw, float eps, const int32_t* positions, const float* cos_sin) {
   B200_CHECK_ARG(head_dim == kD, "attn_decode: head_dim must be 128 (got %d)", head_dim);
   B200_CHECK_ARG(bs > 0 && hq > 0 && hkv > 0 && hq % hkv == 0, "attn_decode: bad bs/hq/hkv %d/%d/%d",
                  bs, hq, hkv);
@@ -388,7 +390,9 @@ extern "C" int b200_attn_decode(const void* q, int64_t q_row_stride, const void*
   if (g_decode_impl.load() == 1)
     return launch_decode_tc(q, q_row_stride, k, k_row_stride, v, v_row_stride, k_cache, v_cache, out_loc,
                             slot_table, slot_table_stride, seq_lens, decode_plan, bs, hq, hkv, num_slots,
-                            page_size, scale_log2, out, part_o, part_ml, counters, dtype, st);
+                            page_size, scale_log2, out, part_o, part_ml, counters, dtype, st, fuse, qw, kw,
+                            eps, positions, cos_sin);
+  B200_CHECK_ARG(!fuse, "attn_decode_fused: only the tcgen05 kernel (decode_impl = 1) fuses qk-norm + RoPE");
 #define FILL(T_)                                                                                  \
   DecodeParams<T_> p{(const T_*)q, q_row_stride, (const T_*)k, k_row_stride, (const T_*)v,        \
                      v_row_stride, (T_*)k_cache, (T_*)v_cache, out_loc, slot_table,               \
@@ -403,4 +407,39 @@ extern "C" int b200_attn_decode(const void* q, int64_t q_row_stride, const void*
 #undef FILL
   set_error("attn_decode: bad dtype %d", dtype);
   return 1;
+}
+
+extern "C" int b200_attn_decode(const void* q, int64_t q_row_stride, const void* k,
+                                int64_t k_row_stride, const void* v, int64_t v_row_stride,
+                                void* k_cache, void* v_cache, int64_t num_slots, int page_size,
+                                const int32_t* out_loc,
+                                const int32_t* slot_table, int64_t slot_table_stride,
+                                const int32_t* seq_lens, const int32_t* decode_plan, int bs, int hq,
+                                int hkv, int head_dim, float scale, void* out, void* workspace,
+                                size_t workspace_bytes, int dtype, void* stream) {
+  return attn_decode_impl(q, q_row_stride, k, k_row_stride, v, v_row_stride, k_cache, v_cache, num_slots,
+                          page_size, out_loc, slot_table, slot_table_stride, seq_lens, decode_plan, bs, hq, hkv,
+                          head_dim, scale, out, workspace, workspace_bytes, dtype, stream, 0, nullptr, nullptr,
+                          0.f, nullptr, nullptr);
+}
+
+extern "C" int b200_attn_decode_fused(const void* q, int64_t q_row_stride, const void* k,
+                                      int64_t k_row_stride, const void* v, int64_t v_row_stride,
+                                      const void* q_weight, const void* k_weight, float eps,
+                                      const int32_t* positions, const float* cos_sin_cache,
+                                      void* k_cache, void* v_cache, int64_t num_slots, int page_size,
+                                      const int32_t* out_loc, const int32_t* slot_table,
+                                      int64_t slot_table_stride, const int32_t* seq_lens,
+                                      const int32_t* decode_plan, int bs, int hq, int hkv, int head_dim,
+                                      float scale, void* out, void* workspace, size_t workspace_bytes,
+                                      int dtype, void* stream) {
+  B200_CHECK_ARG(positions != nullptr && cos_sin_cache != nullptr,
+                 "attn_decode_fused: positions / cos_sin_cache must not be NULL");
+  B200_CHECK_ARG(((uintptr_t)q_weight % 16) == 0 && ((uintptr_t)k_weight % 16) == 0 &&
+                     ((uintptr_t)cos_sin_cache % 16) == 0,
+                 "attn_decode_fused: weights / cos_sin_cache must be 16-byte aligned");
+  return attn_decode_impl(q, q_row_stride, k, k_row_stride, v, v_row_stride, k_cache, v_cache, num_slots,
+                          page_size, out_loc, slot_table, slot_table_stride, seq_lens, decode_plan, bs, hq, hkv,
+                          head_dim, scale, out, workspace, workspace_bytes, dtype, stream, 1, q_weight, k_weight,
+                          eps, positions, cos_sin_cache);
 }

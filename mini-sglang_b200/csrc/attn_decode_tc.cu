@@ -25,12 +25,20 @@
 //            operand, O^T tiles are read back and accumulated in registers with the online-softmax
 //            rescale; row sums are kept per thread and reduced once per unit.
 //
+// Fused pre-attention (p.fuse, b200_attn_decode_fused): q and the new k row arrive RAW (straight from the
+// qkv projection); the Q loader applies the per-head RMSNorm + neox RoPE of layers/attention.py:50-54 with
+// the arithmetic of qknorm_rope_kernel (qknorm_rope.cuh, bit for bit) while it builds the swizzled Q
+// operand, and hands the roped q / k rows the epilogue needs (new-token score, append payload) to the
+// softmax warps through a small smem ring -- the separate qk-norm + RoPE launch disappears and q / k are
+// never written back to global memory (only the pool row of the new token is).
+//
 // The token appended by this launch is handled without touching the pool copy that is being
 // written: its score / value come straight from the k/v inputs on CUDA cores in the epilogue of
 // the unit that owns position kv_len-1 (which also performs the append).
 #include "b200attn.h"
 #include "combine.cuh"
 #include "common.cuh"
+#include "qknorm_rope.cuh"
 #include "sm100.cuh"
 
 #include <type_traits>
@@ -57,6 +65,8 @@ constexpr int kNPad = 16;                   // UMMA N (query heads of the group,
 constexpr int kNumS = 4;                    // max S^T buffers in TMEM (QK^T look-ahead), runtime p.num_s
 constexpr int kTmemCols = 128;              // S^T: kNumS x 16 columns, O^T: 2 x 16 columns
 constexpr int kMaxUnitsSmem = 96;          // per-CTA work units decoded once into smem
+constexpr int kEpiSlots = 4;                // fused mode: roped (q heads, new k) rows in flight to the epilogue
+constexpr int kEpiSlotBytes = 9 * kD * 2;   // up to 8 q heads + the k row, 128 x 16-bit each
 
 struct Smem {
   // offsets from the 1024-aligned base
@@ -64,13 +74,15 @@ struct Smem {
   static constexpr int vring = kStages * kStageBytes;      // V tiles, released after PV
   static constexpr int qbuf = 2 * kStages * kStageBytes;
   static constexpr int pbuf = qbuf + 2 * kQBufBytes;
-  static constexpr int bars = pbuf + 2 * kPBufBytes;      // 32 mbarriers
-  static constexpr int tmem_ptr = bars + 32 * 8;
+  static constexpr int bars = pbuf + 2 * kPBufBytes;      // 40 mbarriers
+  static constexpr int tmem_ptr = bars + 40 * 8;
   static constexpr int red = tmem_ptr + 16;               // floats: [2][4][16] tile max, [2][4][16] row sums, [2][4][16] new-token dots
   static constexpr int units = red + (2 * 4 * 16 + 2 * 4 * 16 + 2 * 4 * 16) * 4;  // decoded work units
-  static constexpr int total = units + kMaxUnitsSmem * 40;
+  static constexpr int epi = units + kMaxUnitsSmem * 40;   // fused mode: kEpiSlots x [9][128] 16-bit
+  static constexpr int total = epi + kEpiSlots * kEpiSlotBytes;
 };
-enum Bar { kFullK = 0, kEmptyK = 3, kFullV = 6, kEmptyV = 9, kSFull = 12, kPFull = 16, kOFull = 18, kQFull = 20, kQEmpty = 22, kFinFull = 24, kFinEmpty = 28 };
+static_assert(Smem::total + 1024 <= 232448, "decode kernel shared memory exceeds the 227 KB per-CTA limit");
+enum Bar { kFullK = 0, kEmptyK = 3, kFullV = 6, kEmptyV = 9, kSFull = 12, kPFull = 16, kOFull = 18, kQFull = 20, kQEmpty = 22, kFinFull = 24, kFinEmpty = 28, kEpiFull = 32, kEpiEmpty = 36 };
 constexpr int kFinRing = 4;  // units in flight between the softmax warps and the combiner warp
 
 template <typename T>
@@ -99,6 +111,13 @@ struct Params {
   float* part_o;
   float* part_ml;
   int* counters;  // [bs][hkv] split-KV arrival counters, zero between launches
+  // fused pre-attention (fuse = 1): q / k_new are raw; norm weights may be NULL (models without qk-norm)
+  int fuse;
+  const T* qw;
+  const T* kw;
+  float eps;
+  const int32_t* positions;
+  const float* cos_sin;  // fp32 [max_pos][128] = cos | sin
 };
 
 struct Unit {
@@ -159,6 +178,10 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     for (int b = 0; b < kFinRing; ++b) {
       mbar_init(bar(kFinFull + b), 128);
       mbar_init(bar(kFinEmpty + b), 1);
+    }
+    for (int b = 0; b < kEpiSlots; ++b) {
+      mbar_init(bar(kEpiFull + b), 1);
+      mbar_init(bar(kEpiEmpty + b), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(kPFull + b), 128);
@@ -375,23 +398,53 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     }
   } else if (warp == kWarpQ) {
     // ============================================================ Q loader
-    uint32_t unit_count = 0;
+    uint32_t unit_count = 0, epi_count = 0;
     for (int k = 0; k < n_rounds; ++k) {
       const Unit u = unit_at(k);
-      if (u.n_tiles <= 0) continue;
-      const uint32_t qb = unit_count & 1;
-      mbar_wait(bar(kQEmpty + qb), ((unit_count >> 1) & 1) ^ 1);
+      if (u.n_tiles < 0) continue;
+      const bool need_q = u.n_tiles > 0;                 // the tensor core needs the Q operand
+      const bool need_epi = p.fuse && u.last_chunk;      // the epilogue needs roped q / k rows
+      if (!need_q && !need_epi) continue;
+      const uint32_t qb = unit_count & 1, es = epi_count % kEpiSlots;
+      if (need_q) mbar_wait(bar(kQEmpty + qb), ((unit_count >> 1) & 1) ^ 1);
+      if (need_epi) mbar_wait(bar(kEpiEmpty + es), ((epi_count / kEpiSlots) & 1) ^ 1);
       uint8_t* qdst = smem + Smem::qbuf + qb * kQBufBytes;
-      for (int idx = lane; idx < G * 16; idx += kWarp) {
-        const int g = idx >> 4, cc = idx & 15;
-        const Vec8 v = *reinterpret_cast<const Vec8*>(p.q + (int64_t)u.r * p.q_rs +
-                                                      (int64_t)(u.h * G + g) * kD + cc * 8);
-        *reinterpret_cast<Vec8*>(qdst + (cc >> 3) * 2048 + sw128_offset(g, cc & 7)) = v;
+      if (!p.fuse) {
+        for (int idx = lane; idx < G * 16; idx += kWarp) {
+          const int g = idx >> 4, cc = idx & 15;
+          const Vec8 v = *reinterpret_cast<const Vec8*>(p.q + (int64_t)u.r * p.q_rs +
+                                                        (int64_t)(u.h * G + g) * kD + cc * 8);
+          *reinterpret_cast<Vec8*>(qdst + (cc >> 3) * 2048 + sw128_offset(g, cc & 7)) = v;
+        }
+      } else {
+        // per-head RMSNorm + RoPE on 16-lane groups, two rows per pass: the G q heads of the group and,
+        // for the unit that owns the new token, its k row (row index G).  Uniform trip count: the
+        // shuffles inside qknorm_rope_lanes need the whole warp.
+        uint8_t* edst = smem + Smem::epi + es * kEpiSlotBytes;
+        const float* cs_row = p.cos_sin + (int64_t)__ldg(p.positions + u.r) * kD;
+        const int n_rows = G + (need_epi ? 1 : 0);
+        for (int base = 0; base < n_rows; base += 2) {
+          const int g = base + (lane >> 4), cc = lane & 15;
+          const bool active = g < n_rows, is_k = (g == G);
+          Vec8 xv = {};
+          if (active)
+            xv = is_k ? *reinterpret_cast<const Vec8*>(p.k_new + (int64_t)u.r * p.k_rs + u.h * kD + cc * 8)
+                      : *reinterpret_cast<const Vec8*>(p.q + (int64_t)u.r * p.q_rs + (int64_t)(u.h * G + g) * kD + cc * 8);
+          const Vec8 rv = qknorm_rope_lanes<T, 16, true>(xv, cc, is_k ? p.kw : p.qw, p.eps, cs_row, active);
+          if (active) {
+            if (!is_k && need_q) *reinterpret_cast<Vec8*>(qdst + (cc >> 3) * 2048 + sw128_offset(g, cc & 7)) = rv;
+            if (need_epi) *reinterpret_cast<Vec8*>(edst + g * (kD * 2) + cc * 16) = rv;
+          }
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kQFull + qb));
-      ++unit_count;
+      if (lane == 0) {
+        if (need_q) mbar_arrive(bar(kQFull + qb));
+        if (need_epi) mbar_arrive(bar(kEpiFull + es));
+      }
+      if (need_q) ++unit_count;
+      if (need_epi) ++epi_count;
     }
   } else if (warp >= 4 && warp < 8) {
     // ============================================================ softmax / accumulate (128 threads)
@@ -399,7 +452,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     const int cw = warp - 4;           // TMEM lane quadrant of this warp
     const uint32_t lane_base = (uint32_t)(cw * 32) << 16;
     float* red_max = red;              // [2][4][16], by tile parity
-    uint32_t tile_count = 0, fin_count = 0, unit_par = 0;
+    uint32_t tile_count = 0, fin_count = 0, unit_par = 0, epi_fin = 0;
     // State of one unit's online softmax; everything the epilogue needs.
     struct UnitState {
       Unit u;
@@ -432,6 +485,19 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
       float* red_sum = red + 2 * 4 * 16 + unit_par * 64;  // [4][16]
       float* red_new = red + 4 * 4 * 16 + unit_par * 64;  // [4][16]
       unit_par ^= 1;
+      const bool epi = p.fuse && u.last_chunk;
+      const uint32_t es = epi_fin % kEpiSlots;
+      if (epi) {
+        // fused mode: the Q loader left the roped q rows of the group and the roped new k row in the ring
+        mbar_wait(bar(kEpiFull + es), (epi_fin / kEpiSlots) & 1);
+        ++epi_fin;
+        const uint8_t* esrc = smem + Smem::epi + es * kEpiSlotBytes;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          st.q_new[g] = DTypeTraits<T>::to_float(*reinterpret_cast<const T*>(esrc + g * (kD * 2) + ct * 2));
+        st.kn = DTypeTraits<T>::to_float(*reinterpret_cast<const T*>(esrc + G * (kD * 2) + ct * 2));
+        if (ct < 16) st.app_x = *reinterpret_cast<const Vec8*>(esrc + G * (kD * 2) + ct * 16);
+      }
       float pnew[G];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -444,6 +510,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
         }
       }
       named_bar_sync(1, 128);
+      if (epi && ct == 0) mbar_arrive(bar(kEpiEmpty + es));  // every thread has read its ring values
       float l_tot[G];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -525,17 +592,19 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
       if (u.last_chunk) {
         // operands of the appended token's score / value: issue the loads now, use them in the
         // epilogue -- their latency hides behind the tile loop
-        const T* qrow = p.q + (int64_t)u.r * p.q_rs + (int64_t)(u.h * G) * kD + ct;
+        if (!p.fuse) {  // fused mode: roped q / k come from the Q loader's ring in the epilogue
+          const T* qrow = p.q + (int64_t)u.r * p.q_rs + (int64_t)(u.h * G) * kD + ct;
 #pragma unroll
-        for (int g = 0; g < G; ++g) cur.q_new[g] = DTypeTraits<T>::to_float(qrow[g * kD]);
-        cur.kn = DTypeTraits<T>::to_float(p.k_new[(int64_t)u.r * p.k_rs + u.h * kD + ct]);
+          for (int g = 0; g < G; ++g) cur.q_new[g] = DTypeTraits<T>::to_float(qrow[g * kD]);
+          cur.kn = DTypeTraits<T>::to_float(p.k_new[(int64_t)u.r * p.k_rs + u.h * kD + ct]);
+        }
         cur.vn = DTypeTraits<T>::to_float(p.v_new[(int64_t)u.r * p.v_rs + u.h * kD + ct]);
         // fused KV append (threads 0-15: K row, 16-31: V row, 16 bytes each): destination slot and
         // payload are fetched here as well, so the epilogue only issues the store
         if (ct < 32) {
           cur.app_loc = p.out_loc[u.r];
           const T* src = ct < 16 ? p.k_new + (int64_t)u.r * p.k_rs : p.v_new + (int64_t)u.r * p.v_rs;
-          cur.app_x = *reinterpret_cast<const Vec8*>(src + u.h * kD + (ct & 15) * 8);
+          if (!(p.fuse && ct < 16)) cur.app_x = *reinterpret_cast<const Vec8*>(src + u.h * kD + (ct & 15) * 8);
         }
       }
       if (u.n_tiles == 0) {
@@ -743,7 +812,8 @@ int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, c
                      const int32_t* slot_table, int64_t st_stride, const int32_t* seq_lens,
                      const int32_t* plan, int bs, int hq, int hkv, int64_t num_slots, int page_size,
                      float scale_log2, void* out, float* part_o, float* part_ml, int* counters,
-                     int dtype, cudaStream_t st) {
+                     int dtype, cudaStream_t st, int fuse, const void* qw, const void* kw, float eps,
+                     const int32_t* positions, const float* cos_sin) {
   // A batch the plan policy leaves unsplit needs no combine pass: run the in-kernel merge (a no-op
   // then; still correct for a foreign plan that does split) and skip the combine launch.
   int fused = g_decode_fused_combine.load();
@@ -766,7 +836,7 @@ int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, c
   dtc::Params<T_> p{(const T_*)q, q_rs, (const T_*)k, k_rs, (const T_*)v, v_rs, (T_*)k_cache,     \
                     (T_*)v_cache, out_loc, slot_table, st_stride, seq_lens, plan, bs, hq, hkv,    \
                     (int)num_slots, box_rows, num_s, fused, g_decode_defer.load(), scale_log2, (T_*)out,  \
-                    part_o, part_ml, counters};                       \
+                    part_o, part_ml, counters, fuse, (const T_*)qw, (const T_*)kw, eps, positions, cos_sin};  \
   return dtc::launch<T_>(p, st)
   if (dtype == B200_DTYPE_BF16) {
     RUN(__nv_bfloat16);

@@ -43,7 +43,8 @@ constexpr int kD = 128;
 constexpr int kBM = 128;                   // query rows per sub-tile
 constexpr int kBN = 128;                   // keys per tile
 constexpr int kStages = 2;                 // K ring depth = V ring depth
-constexpr int kThreads = 640;              // 4 control warps + 16 softmax warps
+constexpr int kThreadsHalfRow = 640;       // 4 control warps + 16 softmax warps (two threads per query row)
+constexpr int kThreadsFullRow = 384;       // 4 control warps + 8 softmax warps (one thread per query row)
 constexpr int kHalfBytes = 128 * 128;      // [128 rows x 64 cols] bf16, 128B-swizzled: 16 KB
 constexpr int kTileBytes = 2 * kHalfBytes; // 32 KB
 constexpr int kMaxUnitsSmem = 64;
@@ -119,8 +120,25 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 1)
+// tcgen05.ld of 32 columns into r[0..31] (a slice of a larger register array)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+// kFullRow = true: FlashAttention-4 style softmax -- ONE thread per query row (8 softmax warps, register
+// budget raised with setmaxnreg), the whole 128-column score row lives in registers: one TMEM read per
+// tile, no cross-thread max exchange, no named barrier inside the tile loop.
+// kFullRow = false: two threads per query row (16 softmax warps), the round-1 variant, kept for A/B runs.
+template <typename T, bool kFullRow>
+__global__ void __launch_bounds__(kFullRow ? kThreadsFullRow : kThreadsHalfRow, 1)
 attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map_q,
                        const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_v,
@@ -147,7 +165,7 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
   auto pos_of = [&](int k) { return k * grid + ((k & 1) ? grid - 1 - cta : cta); };
 
   // ---------------------------------------------------------------- one-time setup
-  for (int k = tid; k < kMaxUnitsSmem && k < n_rounds; k += kThreads) {
+  for (int k = tid; k < kMaxUnitsSmem && k < n_rounds; k += (int)blockDim.x) {
     const int pos = pos_of(k);
     Unit u;
     u.n_tiles = -1;
@@ -173,7 +191,7 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
     mbar_init(bar(kQEmpty), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(kSFull + s), 1);
-      mbar_init(bar(kPFull + s), 256);
+      mbar_init(bar(kPFull + s), kFullRow ? 128 : 256);
       mbar_init(bar(kOFull + s), 1);
     }
     fence_barrier_init();
@@ -193,7 +211,11 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (warp < 2) {
+  // Register budget (full-row variant): the control warpgroup gives registers up, the softmax warpgroups take
+  // them.  Each setmaxnreg sits at the top of its own branch so that ptxas allocates per role.
+  if (warp < 4) {
+   if constexpr (kFullRow) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+   if (warp < 2) {
     // ============================================================ TMA producers: warp 0 = K (+Q), warp 1 = V
     const int kind = warp;
     const int rb = p.box_rows;
@@ -268,9 +290,12 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
       const int col0 = u.h * kD;
       const bool owner = !p.skip_append && (u.head0 == u.h * group);
       const int own_lo = u.cached + u.q_start, own_hi = u.cached + min(u.q_len, u.q_start + kBM);
-      if (kind == 0) {
-        // the unit's query sub-tiles (rows past the tensor end are zero filled, rows past the
-        // request's end belong to the next request: computed, never stored)
+      // The unit's query sub-tiles are requested right AFTER its first K tile (see the tile loop): the Q
+      // buffer only becomes free once the previous unit's last QK^T has completed, whereas a K ring slot is
+      // usually free earlier -- so the first K tile of the next unit no longer queues behind the Q wait.
+      auto load_q = [&]() {
+        // rows past the tensor end are zero filled, rows past the request's end belong to the next
+        // request: computed, never stored
         mbar_wait(bar(kQEmpty), (unit_count & 1) ^ 1);
         if (lane == 0) {
           mbar_arrive_expect_tx(bar(kQFull), (uint32_t)u.n_sub * kTileBytes);
@@ -280,8 +305,7 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
                           (u.head0 + s) * kD + half * 64, u.q_begin + u.q_start);
         }
         __syncwarp();
-      }
-      ++unit_count;
+      };
       // Positions < cached come from the pool through the slot table; positions >= cached are the
       // tokens of this very forward and are read straight from the k / v inputs (row q_begin + pos -
       // cached), so the attention never depends on the append that warp 3 performs concurrently.
@@ -342,6 +366,7 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
             }
           }
         }
+        if (kind == 0 && t == 0) load_q();
         // tiles issued earlier may have landed by now
         for (int s2 = 0; s2 < kStages; ++s2)
           if (s2 != (int)stage) try_store(s2);
@@ -357,6 +382,7 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
           pend[stage].slots = slots;
         }
       }
+      ++unit_count;
     }
     // tiles still waiting for their append: wait until they have landed, store, drain
     for (int s = 0; s < kStages; ++s)
@@ -396,8 +422,10 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
         for (int kk = 0; kk < 8; ++kk) {
           // B = V (MN-major): 16 keys = two 8-key swizzle atoms (1024 B each); dims 64..127 at +16 KB
           const uint64_t db = make_smem_desc(vb + kk * 2048, kHalfBytes, 1024, kLayoutSW128);
-          // P: keys 0-63 packed in columns 0-31, keys 64-127 in columns 64-95 of the sub-tile
-          umma_f16_ts(d, pa + (kk >> 2) * 64 + (kk & 3) * 8, db, idesc_pv, (!first) || kk > 0);
+          // P (packed 16-bit pairs over the S columns).  full-row softmax: keys 0-127 in columns 0-63;
+          // half-row softmax: keys 0-63 in columns 0-31, keys 64-127 in columns 64-95 of the sub-tile
+          const uint32_t pcol = kFullRow ? (uint32_t)kk * 8 : (uint32_t)((kk >> 2) * 64 + (kk & 3) * 8);
+          umma_f16_ts(d, pa + pcol, db, idesc_pv, (!first) || kk > 0);
         }
         umma_commit(bar(kOFull + s));
       };
@@ -431,7 +459,151 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
         tile_count += u.n_tiles;
       }
     }
-  } else if (warp >= 4) {
+   }
+  } else if (kFullRow) {
+    // ============================================================ softmax: 8 warps, one thread per query row.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // sub-tile A: warps 4-7, B: warps 8-11; warp & 3 = TMEM lane quadrant.
+    const int sub = (warp - 4) >> 2;
+    const int row = (warp & 3) * 32 + lane;         // query row of the sub-tile = TMEM lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_base + sub * 128;        // my 128 score columns
+    const uint32_t o_addr = tmem_base + lane_base + 256 + sub * 128;  // my 128 output columns
+    uint32_t my_tiles = 0;  // tiles this warpgroup processed (barrier phases)
+    for (int k = 0; k < n_rounds; ++k) {
+      const Unit u = unit_at(k);
+      if (u.n_tiles <= 0) continue;
+      if (sub >= u.n_sub) continue;  // odd group size: the B warpgroup sits this unit out
+      const int q_row = u.q_start + row;
+      const int vis_end = min(u.cached + q_row + 1, u.kv_len);  // keys [0, vis_end) are visible
+      float m_used = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < u.n_tiles; ++j, ++my_tiles) {
+        const int tile_begin = j * kBN;
+        mbar_wait(bar(kSFull + sub), my_tiles & 1);
+        tc_fence_after_sync();
+        // visible keys of this row inside the tile form a prefix [0, n_vis); rows of a warp are consecutive,
+        // so lane 0 / lane 31 bound the warp: whole 32-column chunks are skipped, unmasked, or (at most two)
+        // masked element-wise -- warp-uniform branches
+        const int n_vis = max(0, min(kBN, vis_end - tile_begin));
+        const int n_lo = __shfl_sync(0xffffffffu, n_vis, 0), n_hi = __shfl_sync(0xffffffffu, n_vis, 31);
+        uint32_t s[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c * 32 < n_hi) tmem_ld32(s_addr + c * 32, s + c * 32);
+        tmem_wait_ld();
+        // ---- row max
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = c * 32;
+          if (col0 >= n_hi) continue;
+          if (col0 + 32 <= n_lo) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              mx0 = fmaxf(mx0, __uint_as_float(s[col0 + e]));
+              mx1 = fmaxf(mx1, __uint_as_float(s[col0 + e + 1]));
+              mx2 = fmaxf(mx2, __uint_as_float(s[col0 + e + 2]));
+              mx3 = fmaxf(mx3, __uint_as_float(s[col0 + e + 3]));
+            }
+          } else {
+            const int nv = n_vis - col0;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              mx0 = fmaxf(mx0, e < nv ? __uint_as_float(s[col0 + e]) : -INFINITY);
+              mx1 = fmaxf(mx1, e + 1 < nv ? __uint_as_float(s[col0 + e + 1]) : -INFINITY);
+              mx2 = fmaxf(mx2, e + 2 < nv ? __uint_as_float(s[col0 + e + 2]) : -INFINITY);
+              mx3 = fmaxf(mx3, e + 3 < nv ? __uint_as_float(s[col0 + e + 3]) : -INFINITY);
+            }
+          }
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        // ---- the previous PV of this sub-tile has completed (in-order tensor pipe); observe it so that the
+        // phase of kOFull never runs ahead of us, then rescale O if the max moved a lot (lazy correction)
+        if (j > 0) {
+          mbar_wait(bar(kOFull + sub), (my_tiles - 1) & 1);
+          tc_fence_after_sync();
+        }
+        const bool grow = mx > m_used + kRescaleThreshold;   // also true for the first tile (-inf)
+        const float m_new = grow ? mx : m_used;
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? fast_exp2(m_used - m_new) : 1.f;
+          l_run *= alpha;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld_x32(o_addr + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st_x32(o_addr + c * 32, o);
+          }
+          tmem_wait_st();
+        }
+        m_used = m_new;
+        const float m_sub = (m_used == -INFINITY) ? 0.f : m_used;
+        // ---- P = exp2(S*scale - m), row sum, packed 16-bit pairs back to TMEM over my own S columns 0-63
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = c * 32;
+          uint32_t pk[16];
+          if (col0 >= n_hi) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pk[e] = 0u;
+          } else if (col0 + 32 <= n_lo) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const float p0 = fast_exp2(fmaf(__uint_as_float(s[col0 + e]), p.scale_log2, -m_sub));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(s[col0 + e + 1]), p.scale_log2, -m_sub));
+              l0 += p0;
+              l1 += p1;
+              pk[e >> 1] = pack2<T>(p0, p1);
+            }
+          } else {
+            const int nv = n_vis - col0;
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const float p0 = e < nv ? fast_exp2(fmaf(__uint_as_float(s[col0 + e]), p.scale_log2, -m_sub)) : 0.f;
+              const float p1 = e + 1 < nv ? fast_exp2(fmaf(__uint_as_float(s[col0 + e + 1]), p.scale_log2, -m_sub)) : 0.f;
+              l0 += p0;
+              l1 += p1;
+              pk[e >> 1] = pack2<T>(p0, p1);
+            }
+          }
+          tmem_st_x16(s_addr + c * 16, pk);
+        }
+        l_run += l0 + l1;
+        tmem_wait_st();
+        tc_fence_before_sync();
+        mbar_arrive(bar(kPFull + sub));
+      }
+      // ---- epilogue: O / l -> out (my row, 128 columns = 256 contiguous bytes)
+      mbar_wait(bar(kOFull + sub), (my_tiles - 1) & 1);
+      tc_fence_after_sync();
+      const float inv = 1.f / l_run;
+      const bool store = q_row < u.q_len;
+      T* orow = p.out + ((int64_t)(u.q_begin + q_row) * p.hq + (u.head0 + sub)) * kD;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld_x32(o_addr + c * 32, o);
+        tmem_wait_ld();
+        if (store) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            Vec8 w;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              w.w[e] = pack2<T>(__uint_as_float(o[v4 * 8 + 2 * e]) * inv, __uint_as_float(o[v4 * 8 + 2 * e + 1]) * inv);
+            *reinterpret_cast<Vec8*>(orow + c * 32 + v4 * 8) = w;
+          }
+        }
+      }
+      // my O / S reads are complete (tmem_wait_ld); the next unit's PV(0) that overwrites O is gated on
+      // kPFull, which every thread of this warpgroup arrives on only after its own epilogue
+      tc_fence_before_sync();
+    }
+  } else {
     // ============================================================ softmax: 16 warps.
     // sub-tile A: warps 4-7 (score columns 0-63) + 12-15 (columns 64-127); B: warps 8-11 + 16-19.
     // Two threads share a query row (same TMEM lane, different column halves) and exchange only the
@@ -606,7 +778,7 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
 
 template <typename T>
 static int launch(const Params<T>& p, const void* q, int64_t q_rs, int64_t nnz, const void* k_cache,
-                  const void* v_cache, cudaStream_t st) {
+                  const void* v_cache, cudaStream_t st, bool full_row) {
   CUtensorMap nk, nv, nbk, nbv;
   const bool bf16 = std::is_same<T, __nv_bfloat16>::value;
   CUtensorMap mq, mk, mv, bk, bv;
@@ -633,11 +805,16 @@ static int launch(const Params<T>& p, const void* q, int64_t q_rs, int64_t nnz, 
   const size_t smem = Smem::total + 1024;
   static bool configured = false;
   if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel<T>,
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel<T, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_prefill_tc_kernel<T, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  attn_prefill_tc_kernel<T><<<num_sms(), kThreads, smem, st>>>(p, mq, mk, mv, bk, bv, nk, nv, nbk, nbv);
+  if (full_row)
+    attn_prefill_tc_kernel<T, true><<<num_sms(), kThreadsFullRow, smem, st>>>(p, mq, mk, mv, bk, bv, nk, nv, nbk, nbv);
+  else
+    attn_prefill_tc_kernel<T, false><<<num_sms(), kThreadsHalfRow, smem, st>>>(p, mq, mk, mv, bk, bv, nk, nv, nbk, nbv);
   B200_POST_LAUNCH();
   return 0;
 }
@@ -645,6 +822,7 @@ static int launch(const Params<T>& p, const void* q, int64_t q_rs, int64_t nnz, 
 }  // namespace ptc
 
 extern std::atomic<int> g_prefill_skip_append;
+extern std::atomic<int> g_prefill_full_row;
 
 // entry used by b200_attn_prefill (attn_prefill.cu)
 int launch_prefill_tc(const void* q, int64_t q_rs, int64_t nnz, const void* k, const void* v, int64_t kv_rs,
@@ -666,7 +844,7 @@ int launch_prefill_tc(const void* q, int64_t q_rs, int64_t nnz, const void* k, c
   ptc::Params<T_> p{slot_table, st_stride, seq_lens, cu_q, prefill_plan, bs, hq, hkv, (int)num_slots, \
                     box_rows, scale_log2, (T_*)out, (const T_*)k, (const T_*)v, kv_rs, (T_*)k_cache,  \
                     (T_*)v_cache, out_loc, nnz, g_prefill_skip_append.load()};                                                   \
-  return ptc::launch<T_>(p, q, q_rs, nnz, k_cache, v_cache, st)
+  return ptc::launch<T_>(p, q, q_rs, nnz, k_cache, v_cache, st, g_prefill_full_row.load() != 0)
   if (dtype == B200_DTYPE_BF16) {
     RUN(__nv_bfloat16);
   }

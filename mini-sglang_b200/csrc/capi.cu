@@ -27,6 +27,7 @@ std::atomic<int> g_decode_impl{1};
 std::atomic<int> g_prefill_impl{1};
 std::atomic<int> g_prefill_order{0};  // 0 = size-sorted + snake dealing (balanced; measured best), 1 = request-major
 std::atomic<int> g_prefill_skip_append{0};  // debug only
+std::atomic<int> g_prefill_full_row{1};     // 1 = one softmax thread per query row (8 warps), 0 = two (16 warps)
 std::atomic<int> g_decode_lookahead{4};
 // Split-KV policy (measured, profiles/r01_decode_plan_sweep.json): splitting costs a partial (o, m, l)
 // round trip plus the combine pass, so it only pays when whole requests cannot fill the grid.
@@ -50,6 +51,7 @@ extern "C" int b200_set_option(const char* name, int value) {
   if (name != nullptr && std::strcmp(name, "use_pdl") == 0) return b200::g_use_pdl.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_impl") == 0) return b200::g_decode_impl.exchange(value);
   if (name != nullptr && std::strcmp(name, "prefill_skip_append") == 0) return b200::g_prefill_skip_append.exchange(value);
+  if (name != nullptr && std::strcmp(name, "prefill_full_row") == 0) return b200::g_prefill_full_row.exchange(value);
   if (name != nullptr && std::strcmp(name, "prefill_order") == 0) return b200::g_prefill_order.exchange(value);
   if (name != nullptr && std::strcmp(name, "prefill_impl") == 0) return b200::g_prefill_impl.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_lookahead") == 0) return b200::g_decode_lookahead.exchange(value);

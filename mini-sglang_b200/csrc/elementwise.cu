@@ -7,6 +7,7 @@
 // (no reuse), grids sized from the row count.
 #include "b200attn.h"
 #include "common.cuh"
+#include "qknorm_rope.cuh"
 
 namespace b200 {
 
@@ -232,7 +233,6 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(
     float eps, const PosT* __restrict__ positions, const float* __restrict__ cos_sin, int64_t nnz,
     int hq, int hkv, int64_t qrs, int64_t krs) {
   constexpr int kDim = G * 8;
-  constexpr int kHalf = kDim / 2;
   pdl_wait();
   pdl_launch_dependents();
   const int heads = hq + hkv;
@@ -243,49 +243,12 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(
   const int h = active ? (int)(gid % heads) : 0;
   const bool is_q = h < hq;
   T* ptr = is_q ? (q + t * qrs + (int64_t)h * kDim) : (k + t * krs + (int64_t)(h - hq) * kDim);
-  float f[8];
   Vec8 xv = {};
   if (active) xv = *reinterpret_cast<const Vec8*>(ptr + j * 8);
-  unpack8<T>(xv, f);
-  if constexpr (kNorm) {
-    const T* w = is_q ? qw : kw;
-    // the group reduction runs unconditionally: q-head and k-head groups share a warp, so a
-    // full-mask shuffle must not sit behind the per-group `w != nullptr` branch
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (w != nullptr) {  // uniform per group
-      const float rcp = rsqrtf(ss / (float)kDim + eps);
-      float wf[8];
-      Vec8 wv = *reinterpret_cast<const Vec8*>(w + j * 8);
-      unpack8<T>(wv, wf);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = f[i] * rcp * wf[i];
-      // the unfused reference stores the normed value (one rounding) before RoPE reads it
-      Vec8 rounded = pack8<T>(f);
-      unpack8<T>(rounded, f);
-    }
-  }
-  // rotation partner values
-  float p[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) p[i] = __shfl_xor_sync(0xffffffffu, f[i], G / 2);
-  if (active) {
-    const int64_t pos = (int64_t)positions[t];
-    const int ci = (j * 8) % kHalf;
-    const float4* cp = reinterpret_cast<const float4*>(cos_sin + pos * kDim + ci);
-    const float4* sp = reinterpret_cast<const float4*>(cos_sin + pos * kDim + kHalf + ci);
-    float4 c0 = __ldg(cp), c1 = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
-    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-    const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const bool first = j < G / 2;
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = f[i] * c[i] + (first ? -p[i] : p[i]) * s[i];
-    *reinterpret_cast<Vec8*>(ptr + j * 8) = pack8<T>(o);
-  }
+  const T* w = kNorm ? (is_q ? qw : kw) : nullptr;
+  const float* cs_row = cos_sin + (active ? (int64_t)positions[t] : 0) * kDim;
+  const Vec8 out = qknorm_rope_lanes<T, G, kNorm>(xv, j, w, eps, cs_row, active);
+  if (active) *reinterpret_cast<Vec8*>(ptr + j * 8) = out;
 }
 
 template <typename T, typename PosT, bool kNorm>

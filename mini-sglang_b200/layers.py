@@ -127,8 +127,10 @@ class RotaryEmbedding:
 class AttentionLayer:
     """split -> q/k norm -> RoPE -> ``ctx.attn_backend.forward`` (attention.py:18-57).
 
-    ``fuse_pre_attention=True`` runs the norm+RoPE sequence as the single fused launch
-    (``b200_qknorm_rope_inplace``); results are identical to the three-launch sequence.
+    ``fuse_pre_attention=True``: decode batches run norm + RoPE + KV append + attention as ONE launch
+    (``b200_attn_decode_fused``); prefill batches run the norm+RoPE sequence as a single fused launch
+    (``b200_qknorm_rope_inplace``) in front of the attention launch.  Results are bit-identical to the
+    reference's three-launch sequence followed by attention.
     """
 
     def __init__(
@@ -159,10 +161,21 @@ class AttentionLayer:
     def forward(self, qkv: torch.Tensor) -> torch.Tensor:
         ctx = get_global_ctx()
         q, k, v = qkv.split([self.qo_attn_dim, self.kv_attn_dim, self.kv_attn_dim], dim=-1)
-        if self.fuse_pre_attention:
-            eps = self.q_norm.eps if self.q_norm is not None else (
-                self.k_norm.eps if self.k_norm is not None else 0.0
+        eps = self.q_norm.eps if self.q_norm is not None else (
+            self.k_norm.eps if self.k_norm is not None else 0.0
+        )
+        fused_decode = getattr(ctx.attn_backend, "forward_decode_fused", None)
+        if (self.fuse_pre_attention and fused_decode is not None and ctx.batch.is_decode
+                and ctx.batch.positions.dtype == torch.int32):
+            # decode: norm + RoPE + append + attention are ONE launch (q / k stay raw in memory)
+            o = fused_decode(
+                q.view(-1, self.num_qo_heads, self.head_dim), k, v, self.layer_id, ctx.batch,
+                ctx.batch.positions, self.rotary._cos_sin_cache,
+                self.q_norm.weight if self.q_norm is not None else None,
+                self.k_norm.weight if self.k_norm is not None else None, eps,
             )
+            return o.view(-1, self.qo_attn_dim)
+        if self.fuse_pre_attention:
             ops.qknorm_rope_inplace(
                 ctx.batch.positions, q, k, self.head_dim, self.rotary._cos_sin_cache,
                 self.q_norm.weight if self.q_norm is not None else None,

@@ -140,11 +140,15 @@ def test_decode_second_layer_of_pool(b200, native_lib, decode_impl):
     _run_case(b200, page_size=16, hq=16, hkv=8, lens=DECODE_LENS["tiny"], phase="decode", layer=2, layers=3)
 
 
-@pytest.fixture(params=[1, 0], ids=["tcgen05", "mmasync"])
+@pytest.fixture(params=[1, 2, 0], ids=["tcgen05", "tcgen05-halfrow", "mmasync"])
 def prefill_impl(request, b200, native_lib):
-    prev = b200._cabi.set_option("prefill_impl", request.param)
+    """The tcgen05 product kernel with one softmax thread per query row (default) and with two (the
+    round-1 variant, option prefill_full_row = 0), and the mma.sync bring-up kernel."""
+    prev = b200._cabi.set_option("prefill_impl", 0 if request.param == 0 else 1)
+    prev_rows = b200._cabi.set_option("prefill_full_row", 0 if request.param == 2 else 1)
     yield request.param
     b200._cabi.set_option("prefill_impl", prev)
+    b200._cabi.set_option("prefill_full_row", prev_rows)
 
 
 PREFILL_LENS = {
@@ -349,3 +353,95 @@ def test_prefill_unaligned_cached_boundary(b200, native_lib, page_size, prefill_
     K/V tile that straddles cached_len mixes pool rows and rows of this forward's k/v inputs."""
     _run_case(b200, page_size=page_size, hq=16, hkv=8, lens=[(100, 300), (37, 200), (129, 130), (1, 140)],
               phase="prefill")
+
+
+# ------------------------------------------------------------------ fused pre-attention decode
+def _fused_vs_unfused(b200, *, page_size, hq, hkv, lens, with_norm=True, pad_to=None, seed=3, dtype=torch.bfloat16,
+                      force_split=False):
+    """b200_attn_decode_fused (raw q / k in, qk-norm + RoPE + append + attention in ONE launch) must equal
+    ops.qknorm_rope_inplace followed by backend.forward BIT FOR BIT: output, appended K/V rows, and the
+    raw q / k inputs must stay untouched."""
+    from oracle.rope import ref_cos_sin_cache
+
+    max_seq = max(d for _, d in lens) + 8
+    w = make_world(seed=seed, page_size=page_size, hq=hq, hkv=hkv, max_reqs=max(len(lens), pad_to or 0) + 1,
+                   max_seq=max_seq, dtype=dtype)
+    add_requests(w, lens)
+    triples = list(w.reqs)
+    if pad_to:
+        triples += [(w.page_table.shape[0] - 1, 0, 1)] * (pad_to - len(w.reqs))
+    ref_md = o_meta.ref_prepare_metadata(w.page_table, triples, page_size)
+    saved, w.reqs = w.reqs, triples
+    qkv, _, _, _ = make_inputs(w, seed + 1)
+    w.reqs = saved
+    d = w.d
+    cache = ref_cos_sin_cache(d, max(4096, max_seq), 1e6).cuda()
+    g = torch.Generator().manual_seed(seed)
+    qw = (torch.rand(d, generator=g) + 0.5).to(dtype).cuda() if with_norm else None
+    kw = (torch.rand(d, generator=g) + 0.5).to(dtype).cuda() if with_norm else None
+    prev = b200._cabi.set_option("decode_plan_nosplit", 0) if force_split else None
+    try:
+        results = []
+        for fused in (False, True):
+            gw = GpuWorld(b200, w)
+            batch = gw.batch("decode", pad_to=pad_to)
+            batch.positions = torch.from_numpy(ref_md.positions).cuda()
+            batch.out_loc = torch.from_numpy(ref_md.out_loc).cuda()
+            gw.backend.prepare_metadata(batch)
+            x = qkv.cuda()
+            q, k, v = x.split([hq * d, hkv * d, hkv * d], dim=-1)
+            if fused:
+                out = gw.backend.forward_decode_fused(q.view(-1, hq, d), k, v, 0, batch, batch.positions, cache, qw, kw, 1e-6)
+                torch.cuda.synchronize()
+                assert torch.equal(x.cpu().view(torch.int16), qkv.view(torch.int16)), "fused decode modified its raw inputs"
+            else:
+                b200.ops.qknorm_rope_inplace(batch.positions, q, k, d, cache, qw, kw, 1e-6)
+                out = gw.backend.forward(q.view(-1, hq, d), k, v, 0, batch)
+                torch.cuda.synchronize()
+            kc, vc = gw.pool_rows(0)
+            results.append((out.cpu(), kc, vc))
+            b200.core.set_global_ctx(None)
+    finally:
+        if prev is not None:
+            b200._cabi.set_option("decode_plan_nosplit", prev)
+    (o0, k0, v0), (o1, k1, v1) = results
+    n_real = len(lens)
+    assert torch.equal(o0[:n_real].view(torch.int16), o1[:n_real].view(torch.int16)), \
+        f"fused output differs: max |d| {(o0[:n_real].float() - o1[:n_real].float()).abs().max().item():.3e}"
+    slots = torch.from_numpy(ref_md.out_loc[:n_real].astype(np.int64))
+    assert torch.equal(k0[slots].view(torch.int16), k1[slots].view(torch.int16))
+    assert torch.equal(v0[slots].view(torch.int16), v1[slots].view(torch.int16))
+    mask = torch.ones(k0.shape[0], dtype=torch.bool)
+    mask[torch.from_numpy(ref_md.out_loc.astype(np.int64))] = False
+    assert torch.equal(k0[mask].view(torch.int16), k1[mask].view(torch.int16))
+
+
+@pytest.mark.parametrize("page_size", [1, 64])
+@pytest.mark.parametrize("name", list(DECODE_LENS))
+def test_decode_fused_pre_attention_bit_identical(b200, native_lib, page_size, name):
+    _fused_vs_unfused(b200, page_size=page_size, hq=16, hkv=8, lens=DECODE_LENS[name])
+
+
+@pytest.mark.parametrize("hq,hkv", [(8, 8), (40, 8), (8, 1), (2, 1), (7, 1), (6, 2), (3, 1)])
+def test_decode_fused_gqa_groups(b200, native_lib, hq, hkv):
+    _fused_vs_unfused(b200, page_size=16, hq=hq, hkv=hkv, lens=DECODE_LENS["mixed"][:5])
+
+
+def test_decode_fused_without_qk_norm_and_padded(b200, native_lib):
+    """Llama-style layer (no q/k norm weights) and a graph-padded batch of dummy requests (kv_len 1:
+    units that consist of the appended token only)."""
+    _fused_vs_unfused(b200, page_size=16, hq=8, hkv=1, lens=DECODE_LENS["mixed"][:3], with_norm=False)
+    _fused_vs_unfused(b200, page_size=16, hq=16, hkv=8, lens=DECODE_LENS["mixed"][:3], pad_to=8)
+
+
+def test_decode_fused_split_kv_and_many_units(b200, native_lib):
+    """Split-KV (several chunks per request: only the last chunk owns the new token) and more
+    last-chunk units per CTA than ring slots."""
+    _fused_vs_unfused(b200, page_size=64, hq=16, hkv=8, lens=DECODE_LENS["long"] + [(700, 701)], force_split=True)
+    rnd = random.Random(4)
+    lens = [(n - 1, n) for n in (rnd.randint(1, 300) for _ in range(200))]
+    _fused_vs_unfused(b200, page_size=16, hq=16, hkv=8, lens=lens)
+
+
+def test_decode_fused_fp16(b200, native_lib):
+    _fused_vs_unfused(b200, page_size=1, hq=16, hkv=8, lens=DECODE_LENS["mixed"][:4], dtype=torch.float16)
