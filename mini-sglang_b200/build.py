@@ -46,6 +46,13 @@ NVCC_FLAGS = [
 ]
 
 
+def _flags() -> List[str]:
+    """B200_BUILD_BRINGUP=1 adds the two cross-check kernels (cp.async decode, mma.sync prefill) that the
+    parity tests can select with b200_set_option; the product build does not contain them."""
+    extra = ["-DB200_BRINGUP_KERNELS=1"] if os.environ.get("B200_BUILD_BRINGUP", "0") not in ("", "0") else []
+    return NVCC_FLAGS + extra
+
+
 def _nvcc() -> str:
     cand = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
     return cand if Path(cand).exists() else "nvcc"
@@ -56,7 +63,7 @@ def _digest(sources: List[Path]) -> str:
     for f in sorted(list(CSRC.glob("*.cu*")) + list(INCLUDE.glob("*.h"))):
         h.update(f.name.encode())
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     h.update(" ".join(str(s.name) for s in sources).encode())
     return h.hexdigest()
 
@@ -91,7 +98,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     build_dir.mkdir(exist_ok=True)
     for s in srcs:
         o = build_dir / (s.stem + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(INCLUDE), "-I", str(CSRC), "-c", str(s), "-o", str(o)]
+        cmd = [_nvcc(), *_flags(), "-I", str(INCLUDE), "-I", str(CSRC), "-c", str(s), "-o", str(o)]
         if s.name == "capi.cu":
             cmd.insert(1, f'-DB200_BUILD_DIGEST="B200DIGEST:{digest}"')
         if verbose:

@@ -20,6 +20,7 @@
 namespace b200 {
 
 constexpr int kD = 128;          // head_dim
+#ifdef B200_BRINGUP_KERNELS  // cp.async / CUDA-core cross-check kernel: test builds only (B200_BUILD_BRINGUP=1)
 constexpr int kTile = 64;        // kv tokens per pipeline stage
 constexpr int kStages = 3;
 constexpr int kThreads = 128;
@@ -331,6 +332,8 @@ static int launch_decode(const DecodeParams<T>& p, cudaStream_t st) {
   }
 }
 
+#endif  // B200_BRINGUP_KERNELS
+
 }  // namespace b200
 
 using namespace b200;
@@ -393,6 +396,7 @@ static int attn_decode_impl(const void* q, int64_t q_row_stride, const void* k,
                             page_size, scale_log2, out, part_o, part_ml, counters, dtype, st, fuse, qw, kw,
                             eps, positions, cos_sin);
   B200_CHECK_ARG(!fuse, "attn_decode_fused: only the tcgen05 kernel (decode_impl = 1) fuses qk-norm + RoPE");
+#ifdef B200_BRINGUP_KERNELS
 #define FILL(T_)                                                                                  \
   DecodeParams<T_> p{(const T_*)q, q_row_stride, (const T_*)k, k_row_stride, (const T_*)v,        \
                      v_row_stride, (T_*)k_cache, (T_*)v_cache, out_loc, slot_table,               \
@@ -405,6 +409,10 @@ static int attn_decode_impl(const void* q, int64_t q_row_stride, const void* k,
     FILL(__half);
   }
 #undef FILL
+#else
+  set_error("attn_decode: decode_impl = 0 (cp.async bring-up kernel) is not part of this build (B200_BUILD_BRINGUP=1)");
+  return 1;
+#endif
   set_error("attn_decode: bad dtype %d", dtype);
   return 1;
 }

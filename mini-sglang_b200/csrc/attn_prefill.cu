@@ -15,6 +15,7 @@
 namespace b200 {
 
 constexpr int kD = 128;
+#ifdef B200_BRINGUP_KERNELS  // mma.sync cross-check kernel: test builds only (B200_BUILD_BRINGUP=1)
 constexpr int kBM = 64;   // q rows per CTA
 constexpr int kBN = 64;   // kv tokens per tile
 constexpr int kRowBytes = kD * 2;
@@ -318,6 +319,8 @@ static int launch_prefill(const PrefillParams<T>& p, int max_q, cudaStream_t st)
   return 0;
 }
 
+#endif  // B200_BRINGUP_KERNELS
+
 }  // namespace b200
 
 namespace b200 {
@@ -362,6 +365,7 @@ extern "C" int b200_attn_prefill(const void* q, int64_t q_row_stride, const void
     return launch_prefill_tc(q, q_row_stride, nnz, k, v, k_row_stride, k_cache, v_cache, out_loc, slot_table, slot_table_stride,
                              seq_lens, cu_seqlens_q, prefill_plan, bs, hq, hkv, num_slots, page_size,
                              scale_log2, out, dtype, st);
+#ifdef B200_BRINGUP_KERNELS
   // append the new rows first (same stream => ordered before the attention kernel reads them)
   const int64_t row_bytes = (int64_t)hkv * kD * 2;
   if (int rc = b200_store_kv(k_cache, v_cache, row_bytes, k, v, k_row_stride * 2, out_loc, 0, nnz,
@@ -378,4 +382,10 @@ extern "C" int b200_attn_prefill(const void* q, int64_t q_row_stride, const void
                           (const __half*)v_cache, slot_table, slot_table_stride, seq_lens,
                           cu_seqlens_q, bs, hq, hkv, scale_log2, (__half*)out};
   return launch_prefill(p, max_seqlen_q, st);
+#else
+  (void)max_seqlen_q;
+  set_error("attn_prefill: needs a prefill_plan (b200_build_prefill_plan) and a GQA group <= 16; the mma.sync bring-up kernel "
+            "(prefill_impl = 0) is not part of this build (B200_BUILD_BRINGUP=1)");
+  return 1;
+#endif
 }

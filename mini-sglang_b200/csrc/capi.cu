@@ -48,6 +48,11 @@ extern "C" int b200_abi_version(void) { return 7; }
 extern "C" const char* b200_build_digest(void) { return B200_BUILD_DIGEST + 11; }
 
 extern "C" int b200_set_option(const char* name, int value) {
+#ifndef B200_BRINGUP_KERNELS
+  // the cross-check kernels are compiled into test builds only (B200_BUILD_BRINGUP=1)
+  if (name != nullptr && value == 0 && (std::strcmp(name, "decode_impl") == 0 || std::strcmp(name, "prefill_impl") == 0))
+    return -1;
+#endif
   if (name != nullptr && std::strcmp(name, "use_pdl") == 0) return b200::g_use_pdl.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_impl") == 0) return b200::g_decode_impl.exchange(value);
   if (name != nullptr && std::strcmp(name, "prefill_skip_append") == 0) return b200::g_prefill_skip_append.exchange(value);

@@ -18,7 +18,10 @@ def decode_impl(request, b200, native_lib):
     unit epilogue deferred behind the next unit's first tile -- the default -- and strictly in
     order) and the cp.async / CUDA-core bring-up kernel (selected with the debug options)."""
     impl = 0 if request.param == 0 else 1
-    prev = b200._cabi.set_option("decode_impl", impl)
+    try:
+        prev = b200._cabi.set_option("decode_impl", impl)
+    except b200._cabi.B200NativeError:
+        pytest.skip("cross-check kernel not in this build (B200_BUILD_BRINGUP=1)")
     prev_defer = b200._cabi.set_option("decode_defer_epilogue", 0 if request.param == 2 else 1)
     yield impl
     b200._cabi.set_option("decode_impl", prev)
@@ -144,7 +147,10 @@ def test_decode_second_layer_of_pool(b200, native_lib, decode_impl):
 def prefill_impl(request, b200, native_lib):
     """The tcgen05 product kernel with one softmax thread per query row (default) and with two (the
     round-1 variant, option prefill_full_row = 0), and the mma.sync bring-up kernel."""
-    prev = b200._cabi.set_option("prefill_impl", 0 if request.param == 0 else 1)
+    try:
+        prev = b200._cabi.set_option("prefill_impl", 0 if request.param == 0 else 1)
+    except b200._cabi.B200NativeError:
+        pytest.skip("cross-check kernel not in this build (B200_BUILD_BRINGUP=1)")
     prev_rows = b200._cabi.set_option("prefill_full_row", 0 if request.param == 2 else 1)
     yield request.param
     b200._cabi.set_option("prefill_impl", prev)
