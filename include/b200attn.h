@@ -55,6 +55,9 @@ B200_API int b200_device_supported(void);
  *       leaves the batch unsplit.
  *   "decode_defer_epilogue": 1 (default) = a decode unit's epilogue runs after the next unit's first
  *       tile has been handed to the tensor core; 0 = strictly unit after unit.
+ *   "decode_early_kv": 1 (default) = a decode launch that is being captured into a CUDA graph lets its TMA
+ *       producers stream K/V before the predecessor kernel has finished (programmatic dependent launch; the
+ *       metadata and this layer's pool slice are not written inside the graph); 0 = always wait first.
  *   "decode_plan_target": when splitting, aim at target * CTA-hint / kv_heads (request, chunk) items (default 2).
  *   "decode_plan_nosplit": no split-KV once bs * kv_heads * 100 >= value * CTA-hint (default 75; 0 = always split).
  * Returns the previous value, or -1 for an unknown name. */

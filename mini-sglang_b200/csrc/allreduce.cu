@@ -110,6 +110,10 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const Params<T> p)
   const int chunks = p.dim / 8;
   uint8_t* mine = p.base[p.rank];
   uint32_t* ctr = reinterpret_cast<uint32_t*>(mine + p.ctr_off);
+  // programmatic dependent launch: x is the predecessor's output (and the epoch counter was advanced by the
+  // previous all-reduce, complete by transitivity); the successor may begin its own prologue right away
+  pdl_wait();
+  pdl_launch_dependents();
   if (tid == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(ctr) + 1u;
   __syncthreads();
   const uint32_t epoch = s_epoch;
@@ -241,7 +245,7 @@ static int launch(const Comm* c, const void* x, int64_t x_rs, void* out, int64_t
   B200_CHECK_ARG(iters <= 2, "allreduce: dim %d too large (max 16384)", dim);
   const int grid = rows < kMaxCtas ? (int)rows : kMaxCtas;
   const bool norm = residual != nullptr;
-#define L(IT_, N_) allreduce_push_kernel<T, IT_, N_><<<grid, threads, 0, st>>>(p)
+#define L(IT_, N_) B200_CHECK_CUDA(launch_pdl(allreduce_push_kernel<T, IT_, N_>, dim3(grid), dim3(threads), 0, st, p))
   if (iters == 1) {
     if (norm) L(1, true);
     else L(1, false);

@@ -112,6 +112,7 @@ struct Params {
   float* part_ml;
   int* counters;  // [bs][hkv] split-KV arrival counters, zero between launches
   // fused pre-attention (fuse = 1): q / k_new are raw; norm weights may be NULL (models without qk-norm)
+  int early;  // 1: captured launch -- TMA producers do not wait for the predecessor (see the kernel prologue)
   int fuse;
   const T* qw;
   const T* kw;
@@ -196,9 +197,16 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     prefetch_tensormap(&box_v);
   }
   if (warp == kWarpQ) tmem_alloc(sbase + Smem::tmem_ptr, kTmemCols);
-  // PDL: everything above may overlap the tail of the previous kernel in the stream; from here on
-  // its results (and those of every kernel before it) are complete and visible.
-  pdl_wait();
+  // PDL: everything above may overlap the tail of the previous kernel in the stream.
+  //  * p.early == 0 (eager launches): wait here -- from here on the results of every kernel before this one
+  //    (in particular the metadata kernel's plan / seq_lens / slot table) are complete and visible.
+  //  * p.early == 1 (launch captured into a CUDA graph): the metadata was written BEFORE the graph started
+  //    (prepare_for_replay), and the K/V rows this launch streams belong to this layer's pool slice, which
+  //    no other kernel of the graph writes -- so only the roles that consume the predecessor's outputs
+  //    (Q loader: q / k_new; softmax warps: v_new, out_loc operands, output / partial stores; combiner)
+  //    wait, while the TMA producers start streaming K/V at once: prologue, pipeline fill and the
+  //    predecessor's tail (or a small kernel in between, e.g. the TP all-reduce) overlap.
+  if (!p.early) pdl_wait();
   pdl_launch_dependents();
   const int chunk_tokens = p.plan[0];
   const int total_units = p.plan[1] * p.hkv;
@@ -398,6 +406,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     }
   } else if (warp == kWarpQ) {
     // ============================================================ Q loader
+    if (p.early) pdl_wait();
     uint32_t unit_count = 0, epi_count = 0;
     for (int k = 0; k < n_rounds; ++k) {
       const Unit u = unit_at(k);
@@ -448,6 +457,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     }
   } else if (warp >= 4 && warp < 8) {
     // ============================================================ softmax / accumulate (128 threads)
+    if (p.early) pdl_wait();
     const int ct = tid - 128;          // 0..127 = TMEM lane = key within tile = output dim
     const int cw = warp - 4;           // TMEM lane quadrant of this warp
     const uint32_t lane_base = (uint32_t)(cw * 32) << 16;
@@ -690,6 +700,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     // ============================================================ split-KV combiner (one warp)
     // For every multi-chunk unit of this CTA: count in on the (request, kv head) arrival counter;
     // whoever arrives last merges all partials (flash-decoding reduction) and writes the output.
+    if (p.early) pdl_wait();
     if (p.fused_combine) {
       uint32_t fin_count = 0;
       for (int k = 0; k < n_rounds; ++k) {
@@ -804,6 +815,7 @@ static int launch(const Params<T>& p, cudaStream_t st) {
 extern std::atomic<int> g_decode_lookahead;
 extern std::atomic<int> g_decode_fused_combine;
 extern std::atomic<int> g_decode_defer;
+extern std::atomic<int> g_decode_early_kv;
 bool decode_plan_is_unsplit(int bs, int num_kv_heads, int ctas);  // metadata.cu
 
 // entry used by b200_attn_decode (attn_decode.cu)
@@ -830,13 +842,19 @@ int launch_decode_tc(const void* q, int64_t q_rs, const void* k, int64_t k_rs, c
   }
   B200_CHECK_ARG(num_slots > 0 && num_slots < (1ll << 31), "attn_decode: bad num_slots %lld",
                  (long long)num_slots);
+  // K/V streaming ahead of the predecessor: only for launches that are being captured into a graph
+  int early = 0;
+  if (g_decode_early_kv.load()) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) early = 1;
+  }
   B200_CHECK_ARG(st_stride % 4 == 0 && ((uintptr_t)slot_table % 16) == 0,
                  "attn_decode: slot table rows must be 16-byte aligned");
 #define RUN(T_)                                                                                   \
   dtc::Params<T_> p{(const T_*)q, q_rs, (const T_*)k, k_rs, (const T_*)v, v_rs, (T_*)k_cache,     \
                     (T_*)v_cache, out_loc, slot_table, st_stride, seq_lens, plan, bs, hq, hkv,    \
                     (int)num_slots, box_rows, num_s, fused, g_decode_defer.load(), scale_log2, (T_*)out,  \
-                    part_o, part_ml, counters, fuse, (const T_*)qw, (const T_*)kw, eps, positions, cos_sin};  \
+                    part_o, part_ml, counters, early, fuse, (const T_*)qw, (const T_*)kw, eps, positions, cos_sin};  \
   return dtc::launch<T_>(p, st)
   if (dtype == B200_DTYPE_BF16) {
     RUN(__nv_bfloat16);

@@ -36,6 +36,7 @@ std::atomic<int> g_decode_plan_nosplit{75};  // no split once bs * kv_heads * 10
 // 0 = separate combine launch, 1 = the last-arriving CTA merges the partials in the decode launch,
 // 2 = auto: in-kernel (and no combine launch at all) exactly when the policy above does not split.
 std::atomic<int> g_decode_fused_combine{2};
+std::atomic<int> g_decode_early_kv{1};  // captured decode launches stream K/V without waiting for the predecessor
 std::atomic<int> g_decode_defer{1};  // unit epilogue deferred behind the next unit's first tile
 }
 
@@ -62,6 +63,7 @@ extern "C" int b200_set_option(const char* name, int value) {
   if (name != nullptr && std::strcmp(name, "decode_lookahead") == 0) return b200::g_decode_lookahead.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_plan_target") == 0) return b200::g_decode_plan_target.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_plan_nosplit") == 0) return b200::g_decode_plan_nosplit.exchange(value);
+  if (name != nullptr && std::strcmp(name, "decode_early_kv") == 0) return b200::g_decode_early_kv.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_defer_epilogue") == 0) return b200::g_decode_defer.exchange(value);
   if (name != nullptr && std::strcmp(name, "decode_fused_combine") == 0) return b200::g_decode_fused_combine.exchange(value);
   return -1;
