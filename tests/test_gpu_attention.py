@@ -451,3 +451,78 @@ def test_decode_fused_split_kv_and_many_units(b200, native_lib):
 
 def test_decode_fused_fp16(b200, native_lib):
     _fused_vs_unfused(b200, page_size=1, hq=16, hkv=8, lens=DECODE_LENS["mixed"][:4], dtype=torch.float16)
+
+
+# ------------------------------------------------------------------ reference GPU goldens at real shapes
+def _gpu_golden():
+    from pathlib import Path
+
+    path = Path(__file__).parent / "golden" / "reference_gpu_golden.npz"
+    if not path.exists():
+        return None, []
+    import json
+
+    z = np.load(path)
+    return z, json.loads(bytes(z["cases"]).decode())
+
+
+_GOLD, _GOLD_CASES = _gpu_golden()
+
+
+@pytest.mark.skipif(_GOLD is None, reason="tests/golden/reference_gpu_golden.npz not generated yet")
+@pytest.mark.parametrize("case", _GOLD_CASES, ids=[c["name"] for c in _GOLD_CASES])
+def test_attention_against_reference_gpu_goldens(b200, native_lib, case):
+    """Product path vs the outputs of the reference's FlashInfer-fa2 path and, where the page size allows,
+    its TRT-LLM-gen path (tests/golden/make_reference_gpu_golden.py), at the BASELINE head shapes.  One
+    criterion (oracle/tolerance.vs_reference_gpu): |a - b| <= 1e-3 max|b| + one output ulp."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).parent / "golden"))
+    import helpers
+    from make_reference_gpu_golden import build_case
+    from oracle import tolerance
+
+    bf = lambda a: torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)  # noqa: E731
+    w, md, qkv = build_case(case, helpers, o_meta)
+    hq, hkv, d = case["hq"], case["hkv"], 128
+    gw = GpuWorld(b200, w)
+    batch = gw.batch(case["phase"])
+    g = qkv.cuda()
+    qg, kg, vg = g.split([hq * d, hkv * d, hkv * d], dim=-1)
+    batch.out_loc = torch.from_numpy(md.out_loc).cuda()
+    batch.positions = torch.from_numpy(md.positions).cuda()
+    gw.backend.prepare_metadata(batch)
+    out = gw.backend.forward(qg.view(-1, hq, d), kg, vg, 0, batch)
+    torch.cuda.synchronize()
+    got = out[:: case["step"]].cpu()
+    for ref_name in ("fi", "trtllm"):
+        key = f"{case['name']}_{ref_name}"
+        if key not in _GOLD:
+            continue
+        want = bf(_GOLD[key])
+        err = tolerance.vs_reference_gpu(got, want)
+        assert err <= tolerance.GPU_REL_TOL, f"{key}: excess error {err:.3e} (gate {tolerance.GPU_REL_TOL})"
+
+
+# ------------------------------------------------------------------ per-CTA unit lists longer than their smem cache
+def test_decode_more_units_than_the_smem_unit_cache(b200, native_lib):
+    """kMaxUnitsSmem = 96 units per CTA are decoded into shared memory; beyond that the roles decode
+    units on the fly (attn_decode_tc.cu unit_at).  2000 short requests x 8 kv heads = 16 000 units > 96 x 148."""
+    rnd = random.Random(11)
+    lens = [(n - 1, n) for n in (rnd.randint(1, 9) for _ in range(2000))]
+    _run_case(b200, page_size=16, hq=16, hkv=8, lens=lens, phase="decode", max_seq=32)
+
+
+def test_prefill_more_units_than_the_smem_unit_cache(b200, native_lib):
+    """Same for the prefill kernel (kMaxUnitsSmem = 64): 1250 two-token extends x 8 kv heads = 10 000 units."""
+    lens = [(3, 5)] * 1250
+    _run_case(b200, page_size=1, hq=16, hkv=8, lens=lens, phase="prefill", max_seq=32)
+
+
+def test_prefill_q_len_4096(b200, native_lib):
+    """One 4096-token prompt at the GQA-8 tp-shard shape (32 query tiles x 32 K/V tiles), a chunked
+    continuation on top of a long cached prefix, and a 2048-token prompt at the Qwen3-0.6B shape."""
+    _run_case(b200, page_size=64, hq=8, hkv=1, lens=[(0, 4096)], phase="prefill")
+    _run_case(b200, page_size=64, hq=8, hkv=1, lens=[(4096, 4352), (2048, 4096)], phase="prefill")
+    _run_case(b200, page_size=64, hq=16, hkv=8, lens=[(0, 2048)], phase="prefill")
