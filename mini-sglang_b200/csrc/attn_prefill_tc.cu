@@ -212,9 +212,11 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
   const uint32_t tmem_base = *tmem_ptr_s;
 
   // Register budget (full-row variant): the control warpgroup gives registers up, the softmax warpgroups take
-  // them.  Each setmaxnreg sits at the top of its own branch so that ptxas allocates per role.
+  // them.  Each setmaxnreg sits at the top of its own branch so that ptxas allocates per role.  The pool is what
+  // the CTA was launched with (384 threads x 168 registers = 64 512, NOT the 65 536 of the SM): 128 x 72 +
+  // 256 x 208 = 62 464 fits; a request beyond the pool would block in setmaxnreg.inc forever.
   if (warp < 4) {
-   if constexpr (kFullRow) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+   if constexpr (kFullRow) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
    if (warp < 2) {
     // ============================================================ TMA producers: warp 0 = K (+Q), warp 1 = V
     const int kind = warp;
