@@ -251,6 +251,34 @@ def patch_flashinfer_entry_points() -> int:
     return len(table)
 
 
+def install_into_minisgl(norm_rope: bool = True, row_gather: bool = True) -> bool:
+    """One call, before ``LLM(...)`` / ``Engine(...)``: makes the reference build its model with the sm_100a
+    norm / RoPE kernels and use the sm_100a row gather, with zero edits to the reference.
+
+    ``Engine.__init__`` asserts that CUDA is not initialised yet (engine/engine.py:31) and importing
+    ``flashinfer`` initialises it, so the FlashInfer names cannot be re-bound up front.  Instead the module
+    attribute ``minisgl.engine.engine.create_model`` (engine.py:12, called at engine.py:50-51 after the device
+    is set and before the decode graphs are captured at engine.py:100) is wrapped: the wrapper re-binds the
+    FlashInfer entry points (:func:`patch_flashinfer_entry_points`) and then calls the reference's own
+    ``create_model``.  Returns False when the reference is not importable."""
+    try:
+        import minisgl.engine.engine as ref_engine
+    except ImportError:
+        return False
+    if row_gather:
+        patch_minisgl_kernels()
+    if norm_rope and not getattr(ref_engine.create_model, "_b200_wrapped", False):
+        real_create_model = ref_engine.create_model
+
+        def create_model_with_b200_layers(*args, **kwargs):
+            patch_flashinfer_entry_points()
+            return real_create_model(*args, **kwargs)
+
+        create_model_with_b200_layers._b200_wrapped = True  # type: ignore[attr-defined]
+        ref_engine.create_model = create_model_with_b200_layers
+    return True
+
+
 def restore_flashinfer_entry_points() -> None:
     import flashinfer
 

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--graph", action="store_true",
                     help="time a captured graph of --layers launches (what the engine replays) instead of eager "
                          "launches, which are host-bound below ~30 us per layer")
+    ap.add_argument("--out", default="gpurun_out/decode_sweep.json")
     ap.add_argument("--opts", default="", help="extra option sets to cross with the sweep: 'a=1,b=2;a=0' (';' separates sets)")
     args = ap.parse_args()
     bench.L = args.layers
@@ -101,8 +102,9 @@ def main():
                 if best is None or us < best["us"]:
                     best = row
             print("BEST", json.dumps(best), flush=True)
-    os.makedirs(ROOT / "gpurun_out", exist_ok=True)
-    (ROOT / "gpurun_out" / "decode_sweep.json").write_text(json.dumps(rows))
+    out = ROOT / args.out
+    out.parent.mkdir(parents=True, exist_ok=True)
+    out.write_text(json.dumps(rows))
     for row in rows:
         print(json.dumps(row))
 
