@@ -47,8 +47,8 @@ B200_API int b200_device_supported(void);
 /* Kernel selection knobs (debug / cross-checking only; defaults are the product path):
  *   "decode_impl": 1 = tcgen05 + TMA kernel (default), 0 = cp.async / CUDA-core kernel.
  *   "prefill_impl": 1 = tcgen05 kernel (default, needs prefill_plan), 0 = mma.sync bring-up kernel.
- *   "prefill_full_row": 1 (default) = tcgen05 prefill with one softmax thread per query row (8 warps, whole score
- *       row in registers); 0 = two threads per row (16 warps), the round-1 variant.
+ *   "prefill_full_row": 1 = tcgen05 prefill with one softmax thread per query row (8 warps, whole score row in
+ *       registers, setmaxnreg); 0 (default, measured faster) = two threads per row (16 warps).
  *   "decode_lookahead": S^T buffers the UMMA issuer may run ahead (2..4, default 4).
  *   "decode_fused_combine": 0 = separate combine launch, 1 = merge split-KV partials inside the decode
  *       launch, 2 = auto (default): in-kernel, and no combine launch, exactly when the plan policy

@@ -185,7 +185,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
       mbar_init(bar(kEpiEmpty + b), 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar(kPFull + b), 128);
+      mbar_init(bar(kPFull + b), 4);  // one elected arrival per softmax warp
       mbar_init(bar(kOFull + b), 1);
       mbar_init(bar(kQFull + b), 1);
       mbar_init(bar(kQEmpty + b), 1);
@@ -671,7 +671,8 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
         }
         fence_proxy_async_smem();   // P^T visible to the tensor core
         tc_fence_before_sync();     // our tcgen05.ld of S^T is ordered before the next QK overwrite
-        mbar_arrive(bar(kPFull + (tc & 1)));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kPFull + (tc & 1)));  // one arrival per warp instead of 32 smem atomics
         if (j > 0) {
           retire(tc - 1, cur.alpha_last);
         } else if (pending) {

@@ -191,7 +191,7 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
     mbar_init(bar(kQEmpty), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(kSFull + s), 1);
-      mbar_init(bar(kPFull + s), kFullRow ? 128 : 256);
+      mbar_init(bar(kPFull + s), kFullRow ? 4 : 8);  // one elected arrival per softmax warp of the sub-tile
       mbar_init(bar(kOFull + s), 1);
     }
     fence_barrier_init();
@@ -577,7 +577,8 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
         l_run += l0 + l1;
         tmem_wait_st();
         tc_fence_before_sync();
-        mbar_arrive(bar(kPFull + sub));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kPFull + sub));  // every lane's P is in TMEM (wait::st + fence above)
       }
       // ---- epilogue: O / l -> out (my row, 128 columns = 256 contiguous bytes)
       mbar_wait(bar(kOFull + sub), (my_tiles - 1) & 1);
@@ -602,8 +603,9 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
         }
       }
       // my O / S reads are complete (tmem_wait_ld); the next unit's PV(0) that overwrites O is gated on
-      // kPFull, which every thread of this warpgroup arrives on only after its own epilogue
+      // kPFull, which every warp of this warpgroup arrives on only after all its lanes finished the epilogue
       tc_fence_before_sync();
+      __syncwarp();
     }
   } else {
     // ============================================================ softmax: 16 warps.
@@ -736,7 +738,8 @@ attn_prefill_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
         l_run += l0 + l1;
         tmem_wait_st();
         tc_fence_before_sync();
-        mbar_arrive(bar(kPFull + sub));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kPFull + sub));  // every lane's P is in TMEM (wait::st + fence above)
       }
       // ---- epilogue: O / l -> out (my 64 output columns); l = sum of the two half-row sums
       float* lp = red + (2 * 4 + sub * 2) * 128;  // third buffer, after the two parity buffers

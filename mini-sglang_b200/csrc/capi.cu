@@ -27,7 +27,9 @@ std::atomic<int> g_decode_impl{1};
 std::atomic<int> g_prefill_impl{1};
 std::atomic<int> g_prefill_order{0};  // 0 = size-sorted + snake dealing (balanced; measured best), 1 = request-major
 std::atomic<int> g_prefill_skip_append{0};  // debug only
-std::atomic<int> g_prefill_full_row{1};     // 1 = one softmax thread per query row (8 warps), 0 = two (16 warps)
+// 1 = one softmax thread per query row (8 warps, FA4 style), 0 = two (16 warps).  Measured on B200 (round 2,
+// gpurun_out/r2c4): cfg1 prompts 312 vs 340 TF/s, 2 x 4096-token GQA-8 prompts 678 vs 695 TF/s -> default 0.
+std::atomic<int> g_prefill_full_row{0};
 std::atomic<int> g_decode_lookahead{4};
 // Split-KV policy (measured, profiles/r01_decode_plan_sweep.json): splitting costs a partial (o, m, l)
 // round trip plus the combine pass, so it only pays when whole requests cannot fill the grid.

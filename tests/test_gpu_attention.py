@@ -143,10 +143,10 @@ def test_decode_second_layer_of_pool(b200, native_lib, decode_impl):
     _run_case(b200, page_size=16, hq=16, hkv=8, lens=DECODE_LENS["tiny"], phase="decode", layer=2, layers=3)
 
 
-@pytest.fixture(params=[1, 2, 0], ids=["tcgen05", "tcgen05-halfrow", "mmasync"])
+@pytest.fixture(params=[1, 2, 0], ids=["tcgen05-fullrow", "tcgen05", "mmasync"])
 def prefill_impl(request, b200, native_lib):
-    """The tcgen05 product kernel with one softmax thread per query row (default) and with two (the
-    round-1 variant, option prefill_full_row = 0), and the mma.sync bring-up kernel."""
+    """The tcgen05 product kernel with two softmax threads per query row (default) and with one (option
+    prefill_full_row = 1), and the mma.sync bring-up kernel (test builds only)."""
     try:
         prev = b200._cabi.set_option("prefill_impl", 0 if request.param == 0 else 1)
     except b200._cabi.B200NativeError:
