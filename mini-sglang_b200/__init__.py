@@ -6,6 +6,7 @@ Holds only what the attention hot path needs:
 * ``_cabi``       ctypes binding (fails loudly if the library is missing; no CPU fallback)
 * ``ops``         operator-level host API (store_cache, rmsnorm, fused_add_rmsnorm, rope, ...)
 * ``attention``   ``B200AttnBackend`` behind the reference's ``BaseAttnBackend`` interface
+* ``distributed`` one-shot NVLink all-reduce behind the reference's ``DistributedCommunicator`` plug-in point
 * ``kvcache`` / ``layers`` / ``core`` / ``utils``  interface mirrors of the reference types the
   boundary touches, for use where the reference is not installed
 
@@ -13,7 +14,7 @@ The directory name is not a Python identifier: import it with
 ``importlib.import_module("mini-sglang_b200")`` or through the ``minisgl_b200`` shim package.
 """
 
-from . import _cabi, attention, core, kvcache, layers, ops, utils  # noqa: F401
+from . import _cabi, attention, core, distributed, kvcache, layers, ops, utils  # noqa: F401
 from .attention import (  # noqa: F401
     BACKEND_NAME,
     SUPPORTED_ATTENTION_BACKENDS,
@@ -37,6 +38,7 @@ __all__ = [
     "build_native",
     "core",
     "create_attention_backend",
+    "distributed",
     "get_global_ctx",
     "kvcache",
     "layers",
