@@ -654,6 +654,11 @@ def run_ours(args) -> dict:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     wl = set_workload(args.config)
+    if args.tp_shard > 1:  # run ONE rank's shard of a tp-N job on a single GPU (no all-reduce partner)
+        if world != 1:
+            raise SystemExit("--tp-shard is for single-GPU runs")
+        wl.tp_shard = args.tp_shard
+        set_workload(args.config)
     tp_group = None
     if world > 1:
         import faulthandler
@@ -1038,6 +1043,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg1", choices=sorted(WORKLOADS), help="BASELINE.json workload (default: the headline cfg1)")
     ap.add_argument("--page-size", type=int, default=64)
+    ap.add_argument("--tp-shard", type=int, default=0, help="single GPU: run one rank's shard of a tp-N job (heads / N)")
     ap.add_argument("--ref-reqs", type=int, default=8, help="--impl reference: requests sampled per step")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--skip-prefill", action="store_true")
