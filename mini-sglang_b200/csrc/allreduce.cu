@@ -37,7 +37,7 @@ namespace b200 {
 namespace ar {
 
 constexpr int kMaxWorld = 8;
-constexpr int kMaxCtas = 128;
+constexpr int kMaxCtas = 512;  // one CTA per row up to 512 rows: the reduce phase is one row deep
 
 struct Comm {
   int rank, world;
