@@ -24,4 +24,16 @@ done
 timeout 900 python bench.py --steps 40 --warmup 4 > $O/bench_cfg1.json 2> $O/bench_cfg1.err; echo "bench cfg1 rc=$?"; cut -c1-400 $O/bench_cfg1.json
 timeout 900 python bench.py --config cfg2 --steps 20 --warmup 3 --prefill-batches 3 --prefill-layers 8 > $O/bench_cfg2.json 2> $O/bench_cfg2.err; echo "bench cfg2 rc=$?"; cut -c1-400 $O/bench_cfg2.json; tail -2 $O/bench_cfg2.err
 timeout 900 python bench.py --config cfg4 --steps 20 --warmup 3 --prefill-batches 4 --prefill-layers 8 > $O/bench_cfg4.json 2> $O/bench_cfg4.err; echo "bench cfg4 rc=$?"; cut -c1-400 $O/bench_cfg4.json; tail -2 $O/bench_cfg4.err
-ls -la $O | head -50
+# one rank's shard of tp2 / tp4 / tp8 on this GPU (no all-reduce partner): where does the per-layer time go?
+for n in 2 4 8; do
+  timeout 600 python bench.py --tp-shard $n --steps 40 --warmup 4 --skip-prefill --skip-cpu --skip-ref-gpu > $O/bench_shard$n.json 2> $O/bench_shard$n.err; python - <<PY
+import json
+d = json.loads([l for l in open("$O/bench_shard$n.json") if l.startswith("{")][-1])
+r = d["roofline"]
+print("shard $n value", d["value"], "ms/step", d["ms_per_step"], "us/layer", round(d["ms_per_step"] * 1e3 / 28, 1), "| attention-only us/launch", r["us_per_launch"], "frac", r["frac"], "e2e", d["e2e"]["value"])
+PY
+done
+timeout 600 python bench.py --tp-shard 8 --steps 40 --warmup 4 --skip-prefill --skip-cpu --skip-ref-gpu --opt decode_early_kv=0 > $O/bench_shard8_noearly.json 2>/dev/null; cut -c1-200 $O/bench_shard8_noearly.json
+timeout 600 python bench.py --tp-shard 8 --steps 40 --warmup 4 --skip-prefill --skip-cpu --skip-ref-gpu --unfused-pre-attention > $O/bench_shard8_unfused.json 2>/dev/null; cut -c1-200 $O/bench_shard8_unfused.json
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 400 --csv --log-file $O/launches_shard8.csv python bench.py --tp-shard 8 --steps 8 --warmup 3 --skip-prefill --skip-cpu --skip-ref-gpu > /dev/null 2>&1; echo "ncu launches shard8 rc=$?"
+ls -la $O | head -60
