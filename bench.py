@@ -366,6 +366,8 @@ class AttentionPathRunner:
         self.stg_ready = [torch.cuda.Event() for _ in range(2)]
         self.stg_free = [torch.cuda.Event() for _ in range(2)]
         self._e2e_step = 0
+        # host-side cost of a step, by phase (microseconds, accumulated; bench reports the per-step mean)
+        self.host_us = {"inputs_h2d": 0.0, "prepare_metadata": 0.0, "prepare_for_replay": 0.0, "graph_replay": 0.0, "steps": 0}
 
     def pad_bs(self, n: int) -> int:
         return next(b for b in self.bs_list if b >= n)
@@ -461,12 +463,23 @@ class AttentionPathRunner:
                 self.stream.wait_event(self.stg_ready[slot])
                 self.qkv[:bs].copy_(stg[:bs], non_blocking=True)
                 self.stg_free[slot].record(self.stream)
+            t0 = time.perf_counter()
             self.positions[:bs].copy_(pos_h, non_blocking=True)
             self.out_loc[:bs].copy_(loc_h, non_blocking=True)
             batch.positions, batch.out_loc = self.positions[:bs], self.out_loc[:bs]
+            t1 = time.perf_counter()
             self.backend.prepare_metadata(batch)
+            t2 = time.perf_counter()
             self.backend.prepare_for_replay(batch)
+            t3 = time.perf_counter()
             self.graphs[bs].replay()
+            t4 = time.perf_counter()
+            hb = self.host_us
+            hb["inputs_h2d"] += (t1 - t0) * 1e6
+            hb["prepare_metadata"] += (t2 - t1) * 1e6
+            hb["prepare_for_replay"] += (t3 - t2) * 1e6
+            hb["graph_replay"] += (t4 - t3) * 1e6
+            hb["steps"] += 1
             if self.allreduce == "nccl":
                 # the reference's NCCL all-reduce of [nnz, hidden] after o_proj (layers/linear.py:102-106),
                 # one per layer; issued eagerly behind the replay
@@ -705,6 +718,8 @@ def run_ours(args) -> dict:
     for st in warm_steps:
         runner.decode_step(st)
     barrier()
+    for k in runner.host_us:
+        runner.host_us[k] = 0
     launches0 = lib.b200_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tokens = 0
@@ -715,6 +730,7 @@ def run_ours(args) -> dict:
         for st in steps:
             tokens += runner.decode_step(st)
         value_host_ms = (time.perf_counter() - host_t0) * 1e3
+        host_breakdown = {k: round(v / max(runner.host_us["steps"], 1), 1) for k, v in runner.host_us.items() if k != "steps"}
         with torch.cuda.stream(runner.stream):
             ev1.record()
         barrier()
@@ -876,6 +892,7 @@ def run_ours(args) -> dict:
         "metric": f"decode tokens/sec (attention hot path, {L} layers) + prefill TFLOPS, {wl.num_seqs}-seq {wl.model} batch",
         "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 4), "host_enqueue_ms_per_step": round(value_host_ms / args.steps, 4),
+        "host_us_per_step": host_breakdown,
         "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{wl.name}: {wl.model} attention path, {wl.desc}, "
