@@ -739,6 +739,17 @@ def run_ours(args) -> dict:
     graph_launches = sum(runner.graph_launches[runner.pad_bs(len(tr))] for tr in step_triples)
     value = tokens / (ms * 1e-3)
 
+    # ---------------- host cost of a step with an idle GPU (no back-pressure from the pinned staging ring):
+    # what the scheduler thread pays per decode iteration for prepare_metadata / prepare_for_replay / replay
+    for k in runner.host_us:
+        runner.host_us[k] = 0
+    for st in steps[: min(10, len(steps))]:
+        torch.cuda.synchronize()
+        runner.decode_step(st)
+    torch.cuda.synchronize()
+    host_unloaded = {k: round(v / max(runner.host_us["steps"], 1), 1) for k, v in runner.host_us.items() if k != "steps"}
+    host_unloaded["total"] = round(sum(host_unloaded.values()), 1)
+
     # ---------------- e2e: host buffers, copies inside the timed region
     qkv_h = torch.empty(tuple(runner.qkv.shape), dtype=torch.bfloat16).pin_memory()
     qkv_h.copy_(runner.qkv.cpu())
@@ -892,7 +903,7 @@ def run_ours(args) -> dict:
         "metric": f"decode tokens/sec (attention hot path, {L} layers) + prefill TFLOPS, {wl.num_seqs}-seq {wl.model} batch",
         "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 4), "host_enqueue_ms_per_step": round(value_host_ms / args.steps, 4),
-        "host_us_per_step": host_breakdown,
+        "host_us_per_step": host_breakdown, "host_us_per_step_gpu_idle": host_unloaded,
         "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{wl.name}: {wl.model} attention path, {wl.desc}, "
