@@ -137,7 +137,8 @@ class B200AttnBackend(BaseAttnBackend):
         self._retired_workspaces: List[torch.Tensor] = []
         # pinned staging ring for the per-batch (table_idx, cached_len, device_len) triples: re-used, never
         # re-allocated per step; an entry is rewritten only after the copy that read it has completed
-        self._info_ring: List[Tuple[torch.Tensor, "torch.cuda.Event"]] = []
+        self._info_ring: List[tuple] = []  # (pinned int32 tensor, event of its last copy, numpy view)
+        self._layouts: dict = {}
         self._info_next = 0
         self._lib = None
         self._sm_count = 0
@@ -175,18 +176,20 @@ class B200AttnBackend(BaseAttnBackend):
         if len(self._info_ring) < self._INFO_RING:
             cap = max(3 * int(get_global_ctx().page_table.shape[0]), n)
             host = torch.empty(cap, dtype=torch.int32, pin_memory=True)
-            self._info_ring.append((host, torch.cuda.Event()))
+            self._info_ring.append((host, torch.cuda.Event(), host.numpy()))
             slot = len(self._info_ring) - 1
         else:
             slot = self._info_next
             self._info_next = (slot + 1) % self._INFO_RING
             self._info_ring[slot][1].synchronize()  # the copy issued 4 batches ago: long done
             if self._info_ring[slot][0].numel() < n:
-                self._info_ring[slot] = (torch.empty(n, dtype=torch.int32, pin_memory=True), self._info_ring[slot][1])
-        host, ev = self._info_ring[slot]
-        host[:n] = torch.tensor(flat, dtype=torch.int32)
-        dev_info = host[:n].to(self.device, non_blocking=True)
-        ev.record(torch.cuda.current_stream(self.device))
+                host = torch.empty(n, dtype=torch.int32, pin_memory=True)
+                self._info_ring[slot] = (host, self._info_ring[slot][1], host.numpy())
+        host, ev, view = self._info_ring[slot]
+        view[:n] = flat  # python ints -> pinned memory, no intermediate tensor
+        dev_info = torch.empty(n, dtype=torch.int32, device=self.device)
+        dev_info.copy_(host[:n], non_blocking=True)
+        ev.record()
         return dev_info
 
     def prepare_metadata(self, batch) -> None:
@@ -197,7 +200,10 @@ class B200AttnBackend(BaseAttnBackend):
             raise RuntimeError("B200AttnBackend.prepare_metadata needs a CUDA device (no CPU path)")
         dev = self.device
         info = self._upload_req_info(flat)
-        off_seq, off_cuq, off_cuk, off_plan, total = small_block_layout(bs)
+        lay = self._layouts.get(bs)
+        if lay is None:
+            lay = self._layouts[bs] = small_block_layout(bs)
+        off_seq, off_cuq, off_cuk, off_plan, total = lay
         small = torch.empty(total, dtype=torch.int32, device=dev)
         page_table = get_global_ctx().page_table
         width = min(_align(max_k, 4), page_table.shape[1])
