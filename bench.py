@@ -705,11 +705,17 @@ def run_ours(args) -> dict:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms: float) -> float:
+    by_rank = {}
+
+    def max_over_ranks(ms: float, tag: str = "") -> float:
         if world > 1:
             t = torch.tensor([ms], device=dev)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            return float(t.item())
+            parts = [torch.empty_like(t) for _ in range(world)]
+            torch.distributed.all_gather(parts, t)
+            vals = [round(float(x.item()), 3) for x in parts]
+            if tag:
+                by_rank[tag] = vals
+            return max(vals)
         return ms
 
     # ---------------- device-timed value
@@ -734,7 +740,7 @@ def run_ours(args) -> dict:
         with torch.cuda.stream(runner.stream):
             ev1.record()
         barrier()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    ms = max_over_ranks(ev0.elapsed_time(ev1), "value_ms")
     eager_launches = lib.b200_launch_count() - launches0
     graph_launches = sum(runner.graph_launches[runner.pad_bs(len(tr))] for tr in step_triples)
     value = tokens / (ms * 1e-3)
@@ -771,7 +777,7 @@ def run_ours(args) -> dict:
     with torch.cuda.stream(runner.stream):
         e1.record()
     barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), "e2e_ms")
     e2e_value = tokens / (e2e_ms * 1e-3)
 
     # ---------------- roofline of the dominant kernel (decode attention): for every timed step an
@@ -903,7 +909,7 @@ def run_ours(args) -> dict:
         "metric": f"decode tokens/sec (attention hot path, {L} layers) + prefill TFLOPS, {wl.num_seqs}-seq {wl.model} batch",
         "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 4), "host_enqueue_ms_per_step": round(value_host_ms / args.steps, 4),
-        "host_us_per_step": host_breakdown, "host_us_per_step_gpu_idle": host_unloaded,
+        "host_us_per_step": host_breakdown, "host_us_per_step_gpu_idle": host_unloaded, "timed_ms_by_rank": by_rank or None,
         "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{wl.name}: {wl.model} attention path, {wl.desc}, "
