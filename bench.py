@@ -201,8 +201,8 @@ def effective_cpus() -> int:
 
 def load_ncu_traffic() -> dict:
     """DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_ncu_decode_tc_summary.json: one launch of tools/microbench.py decode, iteration 500)."""
-    p = ROOT / "profiles" / "r01_ncu_decode_tc_summary.json"
+    (profiles/r02_ncu_decode_tc_summary.json: one launch of tools/microbench.py decode, iteration 500)."""
+    p = ROOT / "profiles" / "r02_ncu_decode_tc_summary.json"
     try:
         d = json.loads(p.read_text())
 
@@ -212,7 +212,7 @@ def load_ncu_traffic() -> dict:
 
         return {"traffic": int(mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")),
                 "traffic_alg_bytes": 133917 * 4096 + 128 * (2 * 8 * 256 + 2 * 16 * 256),
-                "traffic_source": "profiles/r01_ncu_decode_tc_summary.json (ncu --set full, decode iteration 500, bs=128)"}
+                "traffic_source": "profiles/r02_ncu_decode_tc_summary.json (ncu --set full, decode iteration 500, bs=128)"}
     except Exception:
         return {"traffic": None}
 
