@@ -28,6 +28,7 @@ SOURCES = [
     "tma_host.cu",
     "attn_prefill.cu",
     "attn_prefill_tc.cu",
+    "attn_prefill_v3.cu",
     "allreduce.cu",
 ]
 
