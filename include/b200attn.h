@@ -129,7 +129,8 @@ B200_API int b200_qknorm_rope_inplace(void* q, void* k, const void* q_weight, co
 /* ---------------------------------------------------------------------------------------
  * a2/a3/a4  Metadata on device.  Replaces the host loops of prepare_metadata
  *     (M/attention/fa.py:67-105, fi.py:190-225): from per-request triples
- *     req_info[bs][3] = (table_idx, cached_len, device_len) (int32, device) and the global
+ *     req_info[bs][3] = (table_idx, cached_len, device_len) (int32; device memory or PINNED host memory,
+ *     which the kernels read in place -- no host-to-device copy on the step's critical path) and the global
  *     token-granular page table (M/core.py:103-104) produce
  *       seq_lens[bs]            = device_len
  *       cu_seqlens_q[bs+1]      = exclusive cumsum(device_len - cached_len)
