@@ -455,17 +455,27 @@ class AttentionPathRunner:
                 self._e2e_step += 1
                 if self.staging is None:
                     self.staging = [torch.empty_like(self.qkv) for _ in range(2)]
-                stg = self.staging[slot]
+                    self.staging_idx = [torch.empty((2, self.n_seqs), dtype=torch.int32, device=self.dev) for _ in range(2)]
+                stg, stg_idx = self.staging[slot], self.staging_idx[slot]
                 self.copy_stream.wait_event(self.stg_free[slot])
                 with torch.cuda.stream(self.copy_stream):
+                    # ALL host inputs of the step travel on the copy stream, the small index vectors first: a small
+                    # H2D on the compute stream would queue behind the 29 MB transfer in the DMA engine (that
+                    # head-of-line blocking cost ~1 ms per step, profiles/r02_e2e_probe.json)
+                    stg_idx[0, :bs].copy_(pos_h, non_blocking=True)
+                    stg_idx[1, :bs].copy_(loc_h, non_blocking=True)
                     stg[:bs].copy_(qkv_h[:bs], non_blocking=True)
                     self.stg_ready[slot].record(self.copy_stream)
                 self.stream.wait_event(self.stg_ready[slot])
                 self.qkv[:bs].copy_(stg[:bs], non_blocking=True)
+                t0 = time.perf_counter()
+                self.positions[:bs].copy_(stg_idx[0, :bs], non_blocking=True)
+                self.out_loc[:bs].copy_(stg_idx[1, :bs], non_blocking=True)
                 self.stg_free[slot].record(self.stream)
-            t0 = time.perf_counter()
-            self.positions[:bs].copy_(pos_h, non_blocking=True)
-            self.out_loc[:bs].copy_(loc_h, non_blocking=True)
+            else:
+                t0 = time.perf_counter()
+                self.positions[:bs].copy_(pos_h, non_blocking=True)
+                self.out_loc[:bs].copy_(loc_h, non_blocking=True)
             batch.positions, batch.out_loc = self.positions[:bs], self.out_loc[:bs]
             t1 = time.perf_counter()
             self.backend.prepare_metadata(batch)
