@@ -23,15 +23,30 @@ __global__ void __launch_bounds__(kHeadDim) attn_combine_kernel(const float* __r
   const int32_t* chunk_start = plan + kPlanHeader;
   const int n = chunk_start[r + 1] - chunk_start[r];
   if (n <= 1) return;
+  // Every load of the merge is issued before anything is consumed (their addresses do not depend on one
+  // another): one global round trip instead of three -- the kernel is pure latency at decode sizes.
+  const int64_t idx0 = ((int64_t)r * kMaxSplits) * hq + hh;
+  float mc[kMaxSplits], lc[kMaxSplits], oc[kMaxSplits];
+#pragma unroll
+  for (int c = 0; c < kMaxSplits; ++c) {
+    const bool on = c < n;
+    const int64_t idx = idx0 + (int64_t)c * hq;
+    const float2 ml = on ? __ldcg(reinterpret_cast<const float2*>(part_ml + idx * 2)) : make_float2(-INFINITY, 0.f);
+    mc[c] = ml.x;
+    lc[c] = ml.y;
+    oc[c] = on ? __ldcg(part_o + idx * kHeadDim + d) : 0.f;
+  }
   float m = -INFINITY;
-  for (int c = 0; c < n; ++c)
-    m = fmaxf(m, part_ml[(((int64_t)r * kMaxSplits + c) * hq + hh) * 2]);
+#pragma unroll
+  for (int c = 0; c < kMaxSplits; ++c) m = fmaxf(m, mc[c]);
   float acc = 0.f, l = 0.f;
-  for (int c = 0; c < n; ++c) {
-    const int64_t idx = ((int64_t)r * kMaxSplits + c) * hq + hh;
-    const float w = fast_exp2(part_ml[idx * 2] - m);
-    l += w * part_ml[idx * 2 + 1];
-    acc += w * part_o[idx * kHeadDim + d];
+#pragma unroll
+  for (int c = 0; c < kMaxSplits; ++c) {
+    if (c < n) {  // same accumulation order as before: chunk 0, 1, ...
+      const float w = fast_exp2(mc[c] - m);
+      l += w * lc[c];
+      acc += w * oc[c];
+    }
   }
   out[((int64_t)r * hq + hh) * kHeadDim + d] = DTypeTraits<T>::from_float(acc / l);
 }
