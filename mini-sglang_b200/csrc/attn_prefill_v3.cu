@@ -66,7 +66,7 @@ struct Smem {
   static constexpr int total = units + kMaxUnitsSmem * 48;
 };
 static_assert(Smem::total + 1024 <= 232448, "prefill v3 shared memory exceeds the 227 KB per-CTA limit");
-// kSFull / kPFull: index = sub * 2 + buffer
+// kSFull / kPFull / kOFull: index = sub * 2 + (tile & 1)
 enum Bar { kFullK = 0, kEmptyK = 4, kFullV = 8, kEmptyV = 12, kQFull = 16, kQEmpty = 17, kSFull = 18, kPFull = 22, kOFull = 26 };
 
 template <typename T>
@@ -193,8 +193,8 @@ attn_prefill_v3_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar(kSFull + i), 1);
       mbar_init(bar(kPFull + i), 4);  // one elected arrival per softmax warp of the sub-tile
+      mbar_init(bar(kOFull + i), 1);  // PV(s, j) completes on barrier (s, j & 1)
     }
-    for (int s = 0; s < 2; ++s) mbar_init(bar(kOFull + s), 1);
     fence_barrier_init();
     prefetch_tensormap(&map_q);
     prefetch_tensormap(&map_k);
@@ -410,7 +410,7 @@ attn_prefill_v3_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
                   const uint64_t db = make_smem_desc(vb + kk * 2048, kHalfBytes, 1024, kLayoutSW128);
                   umma_f16_ts(d, pa + kk * 8, db, idesc_pv, (j > 0) || kk > 0);
                 }
-                umma_commit(bar(kOFull + s));
+                umma_commit(bar(kOFull + s * 2 + b));
                 ++pv_cnt[s];
                 // the V tile is dead once every sub-tile has issued its PV for it
                 if (pv_cnt[0] > j && (ns == 1 || pv_cnt[1] > j)) umma_commit(bar(kEmptyV + stage));
@@ -456,7 +456,18 @@ attn_prefill_v3_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
     const uint32_t s_base = tmem_base + lane_base + sub * 128;        // + buffer * 64
     const uint32_t o_addr = tmem_base + lane_base + 256 + sub * 128;  // my 128 output columns
     uint32_t s_uses[2] = {0, 0};  // score tiles consumed per buffer (phase of kSFull)
-    uint32_t o_cnt = 0;           // PV completions observed (phase of kOFull)
+    // PV(j) completes on barrier kOFull[sub][j & 1].  o_deliv[b] = P tiles of parity b delivered so far (each is
+    // followed by exactly one PV completion on barrier b), o_seen[b] = completions observed.  A barrier gets its
+    // next completion only after the P two tiles later has been delivered, and PV(j-2) is observed before P(j) is
+    // delivered, so at most one phase is ever pending -- the parity waits stay unambiguous -- while the wait
+    // itself (a PV issued two softmax passes ago) never blocks.
+    uint32_t o_deliv[2] = {0, 0}, o_seen[2] = {0, 0};
+    auto observe = [&](int bb) {  // all PVs of parity bb whose P has been delivered are complete
+      while (o_seen[bb] < o_deliv[bb]) {
+        mbar_wait(bar(kOFull + sub * 2 + bb), o_seen[bb] & 1);
+        ++o_seen[bb];
+      }
+    };
     for (int k = 0; k < n_rounds; ++k) {
       const Unit u = unit_at(k);
       if (u.n_tiles <= 0) continue;
@@ -505,17 +516,15 @@ attn_prefill_v3_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
           }
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
-        // ---- observe PV(j-1) (keeps the kOFull phase in step; it was issued a whole softmax ago, so this rarely
-        // blocks), then rescale O if the running max moved a lot (lazy correction): PV(j) cannot start before
-        // P(j) is delivered below, so O is quiescent here
-        if (j > 0) {
-          mbar_wait(bar(kOFull + sub), o_cnt & 1);
-          ++o_cnt;
-          tc_fence_after_sync();
-        }
+        // ---- keep the kOFull phases in step: PV(j-2) (same parity; issued two passes ago, never blocks)
+        observe(b);
         const bool grow = mx > m_used + kRescaleThreshold;   // also true for the first tile (-inf)
         const float m_new = grow ? mx : m_used;
         if (j > 0 && __any_sync(0xffffffffu, grow)) {
+          // rare (the running max moved by more than 2^8): O must be quiescent -- PV(j-1) complete, and PV(j)
+          // cannot start before P(j) is delivered below
+          observe(b ^ 1);
+          tc_fence_after_sync();
           const float alpha = grow ? fast_exp2(m_used - m_new) : 1.f;
           l_run *= alpha;
 #pragma unroll
@@ -567,10 +576,11 @@ attn_prefill_v3_kernel(const Params<T> p, const __grid_constant__ CUtensorMap ma
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(kPFull + sub * 2 + b));  // every lane's P is in TMEM
+        ++o_deliv[b];
       }
-      // ---- epilogue: O / l -> out (my row, 128 columns = 256 contiguous bytes)
-      mbar_wait(bar(kOFull + sub), o_cnt & 1);
-      ++o_cnt;
+      // ---- epilogue: O / l -> out (my row, 128 columns = 256 contiguous bytes); every PV of the unit complete
+      observe(0);
+      observe(1);
       tc_fence_after_sync();
       const float inv = 1.f / l_run;
       const bool store = q_row < u.q_len;
