@@ -223,11 +223,12 @@ B200_API int b200_attn_prefill(const void* q, int64_t q_row_stride, const void* 
  *     behind the reference's communication plug-in point DistributedCommunicator.plugins
  *     (M/distributed/impl.py:60-97), called after o_proj / down_proj (M/layers/linear.py:102-106,
  *     122-126), and -- fused form -- the flashinfer.fused_add_rmsnorm that follows
- *     (M/layers/norm.py:32-38).  One-shot "push" algorithm over NVLink peer memory: see
- *     csrc/allreduce.cu.  Every rank must issue the same sequence of calls with the same shapes.
+ *     (M/layers/norm.py:32-38).  One-shot "push" algorithm over NVLink peer memory with the payload as its own
+ *     arrival flag (negative zeros in x are sent as +0.0): see csrc/allreduce.cu.  Every rank must issue the
+ *     same sequence of calls with the same shapes.
  *
  *     Set-up (host, once): each rank allocates a region of b200_ar_region_bytes(world, max_bytes)
- *     with b200_ar_alloc (zero-filled), exports it with b200_ar_ipc_handle (64 opaque bytes), the
+ *     with b200_ar_alloc (initialised: sentinel-filled data, zero counters), exports it with b200_ar_ipc_handle (64 opaque bytes), the
  *     handles are exchanged by the caller (torch.distributed), peers are mapped with b200_ar_ipc_open,
  *     and b200_ar_create receives the `world` base pointers in rank order (bases[rank] = own region;
  *     opened_mask[i] != 0 marks pointers b200_ar_destroy must unmap).

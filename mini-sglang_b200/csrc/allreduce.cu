@@ -8,25 +8,30 @@
 // and optionally the flashinfer.fused_add_rmsnorm that consumes its result
 //   (python/minisgl/layers/norm.py:32-38 via models/qwen3.py:38-41).
 //
-// Design ("push" one-shot, one kernel, one synchronisation phase):
-//   every rank owns a region  data[2 parities][world senders][slot] | flags[world][kMaxCtas] | ctr
-//   that all peers have mapped (CUDA IPC).  CTA b of rank s
-//     1. PUSHES the rows it owns (r = b, b + grid, ...) from x -- any device memory, no staging copy --
-//        into slot[parity][s] of EVERY rank with 16-byte stores over NVLink (posted writes, no round trip),
-//     2. fences (system scope) and releases flag[s][b] = epoch on every rank,
-//     3. acquires flag[0..world)[b] >= epoch in its own region (only its counterpart CTAs on the peers:
-//        no grid-wide barrier), then
-//     4. sums the world slots of its rows in rank order in fp32 (every rank gets bit-identical
-//        results), rounds once to the 16-bit type (= the tensor the reference's all-reduce returns) and
-//        either stores it, or applies  residual <- round(y + residual); out <- rmsnorm(y + residual) * w
-//        with the arithmetic of rmsnorm_row_kernel<.., kFusedAdd> (elementwise.cu), bit for bit.
-//   The epoch is a device-resident counter (advanced by the last CTA of each launch), so the kernel is
-//   CUDA-graph capturable and replays correctly; parities alternate per launch, which is enough because
-//   a rank can only enter launch e+1 after every peer has pushed launch e, i.e. has finished launch e-1.
-//   Waits are bounded (globaltimer): a dead peer traps the kernel instead of hanging the GPU.
+// Design (one-shot "push", flag-in-data / Lamport style: one kernel, no fence, no separate flag):
+//   every rank owns a region  data[2 parities][world senders][slot] | (reserved) | epoch, done
+//   that all peers have mapped (CUDA IPC).  At rest every 16-bit lane of the data region holds the SENTINEL
+//   0x8000 (negative zero).  A thread of CTA b of rank s
+//     1. loads its 16-byte chunk of x (any device memory, no staging copy), replaces -0.0 lanes by +0.0 (so a
+//        payload never contains the sentinel) and STORES it into slot[parity][s] of EVERY rank -- 16-byte
+//        peer stores over NVLink, posted writes, no round trip;
+//     2. polls the same chunk of slot[parity][0..world) in its OWN region (volatile 16-byte loads from L2)
+//        until no lane is the sentinel: the data is its own arrival flag (a 16-byte store lands atomically), so
+//        there is no system-scope fence, no flag store and no flag propagation on the critical path, and no
+//        CTA-level synchronisation at all -- the thread that pushed chunk c is the thread that reduces it;
+//     3. sums the world chunks in rank order in fp32 (every rank gets bit-identical results; == NCCL at world 2
+//        except for the sign of an all-negative-zero sum), rounds once to the 16-bit type (= the tensor the
+//        reference's all-reduce returns), writes the sentinel back into the chunks it consumed, and either
+//        stores the sum or applies  residual <- round(y + residual); out <- rmsnorm(y + residual) * w  with
+//        the arithmetic of rmsnorm_row_kernel<.., kFusedAdd> (elementwise.cu), bit for bit.
+//   The parity alternates per launch and comes from a device-resident epoch (advanced by the last CTA of each
+//   launch), so the kernel is CUDA-graph capturable and replays correctly.  Two parities suffice: a rank can
+//   only push launch e+2 (same parity as e) after it finished launch e+1, i.e. after it received every peer's
+//   e+1 chunks, which those peers sent after completing (reading AND re-arming) launch e.
+//   Polls are bounded (globaltimer): a dead peer traps the kernel instead of hanging the GPU.
 //
-// Bytes per launch and rank: (world) x rows x dim x 2 pushed over NVLink (incl. the local copy),
-// world x rows x dim x 2 read back locally; latency-bound for the <= 512 KB messages of decode.
+// Bytes per launch and rank: world x rows x dim x 2 pushed over NVLink (incl. the local copy), the same amount
+// read back and re-armed locally; latency-bound for the <= 512 KB messages of decode (one NVLink write flight).
 #include "b200attn.h"
 #include "common.cuh"
 
@@ -65,25 +70,33 @@ struct Params {
   uint8_t* base[kMaxWorld];
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ Vec8 ld_cg(const void* p) {
+__device__ __forceinline__ Vec8 ld_volatile16(const void* p) {
   Vec8 r;
-  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3])
-               : "l"(p));
+               : "l"(p)
+               : "memory");
   return r;
+}
+constexpr uint32_t kSentinel2 = 0x80008000u;  // two 16-bit negative zeros
+__device__ __forceinline__ bool has_sentinel(const Vec8& v) {
+  bool hit = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) hit |= ((v.w[i] & 0xffffu) == 0x8000u) | ((v.w[i] >> 16) == 0x8000u);
+  return hit;
+}
+__device__ __forceinline__ Vec8 without_negative_zero(Vec8 v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if ((v.w[i] & 0xffffu) == 0x8000u) v.w[i] &= 0xffff0000u;
+    if ((v.w[i] >> 16) == 0x8000u) v.w[i] &= 0x0000ffffu;
+  }
+  return v;
 }
 
 // block-wide sum with the reduction order of elementwise.cu::block_sum (bit-identical norms)
@@ -119,13 +132,13 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const Params<T> p)
   const uint32_t epoch = s_epoch;
   const size_t parity_off = (size_t)(epoch & 1u) * p.world * p.slot_bytes;
 
-  // ---- 1. push my rows into slot[parity][rank] of every rank (peers first, own copy last)
+  // ---- 1. push my chunks into slot[parity][rank] of every rank (peers first, own copy last)
   for (int r = b; r < p.rows; r += grid) {
 #pragma unroll
     for (int it = 0; it < kIter; ++it) {
       const int c = tid + it * blockDim.x;
       if (c < chunks) {
-        const Vec8 v = *reinterpret_cast<const Vec8*>(p.x + (int64_t)r * p.x_rs + c * 8);
+        const Vec8 v = without_negative_zero(*reinterpret_cast<const Vec8*>(p.x + (int64_t)r * p.x_rs + c * 8));
         const size_t off = parity_off + (size_t)p.rank * p.slot_bytes + ((size_t)r * p.dim + c * 8) * sizeof(T);
         for (int i = 1; i <= p.world; ++i) {
           const int t = (p.rank + i) % p.world;
@@ -134,22 +147,10 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const Params<T> p)
       }
     }
   }
-  __syncthreads();
-  // ---- 2. release: my pushes are visible system-wide before the flag is
-  if (tid < p.world) {
-    __threadfence_system();
-    uint32_t* f = reinterpret_cast<uint32_t*>(p.base[tid] + p.flags_off) + p.rank * kMaxCtas + b;
-    st_release_sys(f, epoch);
-    // ---- 3. acquire the flag of sender `tid` for CTA b in my own region
-    const uint32_t* g = reinterpret_cast<const uint32_t*>(mine + p.flags_off) + tid * kMaxCtas + b;
-    const uint64_t t0 = globaltimer_ns();
-    while ((int32_t)(ld_acquire_sys(g) - epoch) < 0) {
-      if (globaltimer_ns() - t0 > 8000000000ull) __trap();  // 8 s: a peer died
-    }
-  }
-  __syncthreads();
 
-  // ---- 4. reduce in rank order, epilogue
+  // ---- 2. + 3. poll my own region for every sender's chunk (the data is its own flag), reduce in rank order,
+  // re-arm the consumed chunks with the sentinel, epilogue
+  const uint64_t t0 = globaltimer_ns();
   for (int r = b; r < p.rows; r += grid) {
     float f[kIter][8];
     float ss = 0.f;
@@ -162,7 +163,16 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const Params<T> p)
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
         const size_t off = parity_off + ((size_t)r * p.dim + c * 8) * sizeof(T);
         for (int s = 0; s < p.world; ++s) {
-          const Vec8 v = ld_cg(mine + off + (size_t)s * p.slot_bytes);
+          uint8_t* slot = mine + off + (size_t)s * p.slot_bytes;
+          Vec8 v = ld_volatile16(slot);
+          uint32_t spins = 0;
+          while (has_sentinel(v)) {
+            if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > 8000000000ull) __trap();  // 8 s: a peer died
+            v = ld_volatile16(slot);
+          }
+          Vec8 arm;
+          arm.w[0] = arm.w[1] = arm.w[2] = arm.w[3] = kSentinel2;
+          *reinterpret_cast<Vec8*>(slot) = arm;  // ready for the launch after next
           float g[8];
           unpack8<T>(v, g);
 #pragma unroll
@@ -268,10 +278,21 @@ extern "C" size_t b200_ar_region_bytes(int world, size_t max_bytes) {
   return 2 * (size_t)world * slot + ar::align_up((size_t)world * ar::kMaxCtas * 4, 256) + 256;
 }
 
+namespace b200 {
+namespace ar {
+__global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+}  // namespace ar
+}  // namespace b200
+
 extern "C" int b200_ar_alloc(size_t bytes, void** ptr) {
-  B200_CHECK_ARG(ptr != nullptr && bytes > 0, "ar_alloc: bad arguments");
+  B200_CHECK_ARG(ptr != nullptr && bytes >= 512 && bytes % 256 == 0, "ar_alloc: bad arguments");
   B200_CHECK_CUDA(cudaMalloc(ptr, bytes));
-  B200_CHECK_CUDA(cudaMemset(*ptr, 0, bytes));
+  // data region: every 16-bit lane = the sentinel (negative zero); trailing 256 bytes (epoch, done counter) = 0
+  ar::fill_u32_kernel<<<256, 256>>>(static_cast<uint32_t*>(*ptr), (bytes - 256) / 4, ar::kSentinel2);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_CHECK_CUDA(cudaMemset(static_cast<char*>(*ptr) + bytes - 256, 0, 256));
   B200_CHECK_CUDA(cudaDeviceSynchronize());
   return 0;
 }
