@@ -28,7 +28,6 @@ SOURCES = [
     "tma_host.cu",
     "attn_prefill.cu",
     "attn_prefill_tc.cu",
-    "attn_prefill_v3.cu",
     "allreduce.cu",
 ]
 

@@ -828,10 +828,6 @@ static int launch(const Params<T>& p, const void* q, int64_t q_rs, int64_t nnz, 
 
 extern std::atomic<int> g_prefill_skip_append;
 extern std::atomic<int> g_prefill_full_row;
-int launch_prefill_v3(const void* q, int64_t q_rs, int64_t nnz, const void* k, const void* v, int64_t kv_rs,
-                      void* k_cache, void* v_cache, const int32_t* out_loc, const int32_t* slot_table, int64_t st_stride,
-                      const int32_t* seq_lens, const int32_t* cu_q, const int32_t* prefill_plan, int bs, int hq, int hkv,
-                      int64_t num_slots, int box_rows, float scale_log2, void* out, int dtype, cudaStream_t st);
 
 // entry used by b200_attn_prefill (attn_prefill.cu)
 int launch_prefill_tc(const void* q, int64_t q_rs, int64_t nnz, const void* k, const void* v, int64_t kv_rs,
@@ -849,9 +845,6 @@ int launch_prefill_tc(const void* q, int64_t q_rs, int64_t nnz, const void* k, c
     while (box_rows > 8 && (page_size % box_rows) != 0) box_rows >>= 1;
     if (page_size % box_rows != 0) box_rows = 0;
   }
-  if (g_prefill_full_row.load() == 2)  // 64-key tiles, double-buffered score tiles (attn_prefill_v3.cu)
-    return launch_prefill_v3(q, q_rs, nnz, k, v, kv_rs, k_cache, v_cache, out_loc, slot_table, st_stride, seq_lens, cu_q,
-                             prefill_plan, bs, hq, hkv, num_slots, box_rows, scale_log2, out, dtype, st);
 #define RUN(T_)                                                                                    \
   ptc::Params<T_> p{slot_table, st_stride, seq_lens, cu_q, prefill_plan, bs, hq, hkv, (int)num_slots, \
                     box_rows, scale_log2, (T_*)out, (const T_*)k, (const T_*)v, kv_rs, (T_*)k_cache,  \

@@ -143,7 +143,7 @@ def test_decode_second_layer_of_pool(b200, native_lib, decode_impl):
     _run_case(b200, page_size=16, hq=16, hkv=8, lens=DECODE_LENS["tiny"], phase="decode", layer=2, layers=3)
 
 
-@pytest.fixture(params=[3, 1, 2, 0], ids=["tcgen05-v3", "tcgen05-fullrow", "tcgen05", "mmasync"])
+@pytest.fixture(params=[1, 2, 0], ids=["tcgen05-fullrow", "tcgen05", "mmasync"])
 def prefill_impl(request, b200, native_lib):
     """The tcgen05 product kernel with two softmax threads per query row (default) and with one (option
     prefill_full_row = 1), and the mma.sync bring-up kernel (test builds only)."""
@@ -151,7 +151,7 @@ def prefill_impl(request, b200, native_lib):
         prev = b200._cabi.set_option("prefill_impl", 0 if request.param == 0 else 1)
     except b200._cabi.B200NativeError:
         pytest.skip("cross-check kernel not in this build (B200_BUILD_BRINGUP=1)")
-    prev_rows = b200._cabi.set_option("prefill_full_row", {3: 2, 1: 1, 2: 0, 0: 0}[request.param])
+    prev_rows = b200._cabi.set_option("prefill_full_row", 1 if request.param == 1 else 0)
     yield request.param
     b200._cabi.set_option("prefill_impl", prev)
     b200._cabi.set_option("prefill_full_row", prev_rows)
