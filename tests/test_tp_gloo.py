@@ -79,3 +79,79 @@ def test_kv_head_replication_when_tp_exceeds_kv_heads():
     assert b200.utils.div_even(4, 8, allow_replicate=True) == 1  # tp > Hkv: replicated
     with pytest.raises(AssertionError):
         b200.utils.div_even(3, 8, allow_replicate=True)
+
+
+# ------------------------------------------------------------------ all-reduce plug-in: host-side routing
+class _FakeComm:
+    """Stands in for B200AllReduce (which needs GPUs + CUDA IPC): same `fits` rule, counts its calls."""
+
+    def __init__(self, max_bytes):
+        self.max_bytes, self.calls = max_bytes, 0
+
+    def fits(self, x):
+        return x.dtype in (torch.bfloat16, torch.float16) and x.shape[-1] % 8 == 0 and x.numel() * x.element_size() <= self.max_bytes
+
+    def all_reduce(self, x):
+        self.calls += 1
+        dist.all_reduce(x)
+        return x
+
+
+def _plugin_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib
+
+    d_mod = importlib.import_module("mini-sglang_b200.distributed")
+
+    class Fallback:  # the plug-in that was active before (the reference's NCCL path; gloo here)
+        calls = 0
+
+        def all_reduce(self, x):
+            Fallback.calls += 1
+            dist.all_reduce(x)
+            return x
+
+        def all_gather(self, x):
+            parts = [torch.empty_like(x) for _ in range(world)]
+            dist.all_gather(parts, x)
+            return torch.cat(parts)
+
+    comm = _FakeComm(max_bytes=64 * 1024)
+    impl = d_mod.B200DistributedImpl(comm, Fallback())
+    small = torch.full((8, 1024), float(rank + 1), dtype=torch.bfloat16)         # 16 KB: decode-sized -> ours
+    big = torch.full((128, 1024), float(rank + 1), dtype=torch.bfloat16)         # 256 KB: prefill-sized -> fallback
+    odd = torch.full((8, 1023), float(rank + 1), dtype=torch.bfloat16)           # row not a multiple of 16 B -> fallback
+    f32 = torch.full((8, 1024), float(rank + 1), dtype=torch.float32)            # dtype the kernel does not take -> fallback
+    res = [impl.all_reduce(t) for t in (small, big, odd, f32)]
+    gathered = impl.all_gather(torch.full((2, 4), float(rank)))
+    if rank == 0:
+        out.put((comm.calls, Fallback.calls, [float(r.float().mean()) for r in res], gathered.shape))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_allreduce_plugin_routes_by_message_size():
+    """B200DistributedImpl (the reference's DistributedImpl interface, distributed/impl.py:16-21): decode-sized
+    16-bit messages go to the push kernel's communicator, everything else to the previous plug-in."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29731
+    procs = [ctx.Process(target=_plugin_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ours, fallback, means, gshape = out.get(timeout=100)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert ours == 1 and fallback == 3
+    assert means == [3.0, 3.0, 3.0, 3.0]  # 1 + 2 on every element, whichever path carried it
+    assert tuple(gshape) == (4, 4)
+
+
+def test_enable_b200_allreduce_is_a_noop_for_tp1():
+    import importlib
+
+    d_mod = importlib.import_module("mini-sglang_b200.distributed")
+    assert d_mod.enable_b200_allreduce(0, 1, None, "cpu") is None
