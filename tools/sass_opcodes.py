@@ -26,7 +26,7 @@ def main():
             fn = m.group(1)
             per[fn] = collections.Counter()
             continue
-        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\w+\s+)?([A-Za-z0-9_.]+)", line)
         if fn and m:
             per[fn][m.group(1)] += 1
     demangled = subprocess.run(["c++filt"], input="\n".join(per), capture_output=True, text=True).stdout.splitlines()
