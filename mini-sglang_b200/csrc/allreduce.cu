@@ -127,7 +127,12 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const Params<T> p)
   // previous all-reduce, complete by transitivity); the successor may begin its own prologue right away
   pdl_wait();
   pdl_launch_dependents();
-  if (tid == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(ctr) + 1u;
+  if (tid == 0) {
+    // epoch of this launch = stored epoch + 1 (acquire: the count-in below cannot overtake this read)
+    uint32_t e;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(ctr) : "memory");
+    s_epoch = e + 1u;
+  }
   __syncthreads();
   const uint32_t epoch = s_epoch;
   const size_t parity_off = (size_t)(epoch & 1u) * p.world * p.slot_bytes;
@@ -146,6 +151,15 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const Params<T> p)
         }
       }
     }
+  }
+
+  // Every CTA counts in after reading the epoch; the CTA that counts in last knows that every CTA of the launch
+  // has read the old value and advances it for the next launch.  Done here, between the push and the poll, the
+  // atomic's round trip hides behind the NVLink flight of the data instead of extending the kernel's tail.
+  if (tid == 0 && atomicAdd(ctr + 1, 1u) == (uint32_t)grid - 1u) {
+    ctr[1] = 0u;
+    __threadfence();
+    *reinterpret_cast<volatile uint32_t*>(ctr) = epoch;
   }
 
   // ---- 2. + 3. poll my own region for every sender's chunk (the data is its own flag), reduce in rank order,
@@ -214,16 +228,6 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const Params<T> p)
     }
   }
 
-  // ---- the last CTA of the launch advances the epoch (every CTA has read it: all have arrived)
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    if (atomicAdd(ctr + 1, 1u) == (uint32_t)grid - 1u) {
-      ctr[1] = 0u;
-      __threadfence();
-      *reinterpret_cast<volatile uint32_t*>(ctr) = epoch;
-    }
-  }
 }
 
 template <typename T>
