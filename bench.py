@@ -733,6 +733,15 @@ def run_ours(args) -> dict:
     warm_steps = [runner.schedule_step(sched.live(it)) for it in warm_iters]
     for st in warm_steps:
         runner.decode_step(st)
+    # A CUDA graph is uploaded to the device on its FIRST launch (milliseconds, and different on every rank): every
+    # distinct captured graph the timed steps replay is launched once here, as a serving engine's graphs are warm
+    # after the first seconds (at tp8 a cold first launch per batch size cost more than the step itself and made
+    # the ranks' timed regions differ by 20 ms, profiles/r02_bench_tp8_cold_graphs.json).
+    seen_bs = set()
+    for st in steps:
+        if st[0].padded_size not in seen_bs:
+            seen_bs.add(st[0].padded_size)
+            runner.decode_step(st)
     barrier()
     for k in runner.host_us:
         runner.host_us[k] = 0
@@ -926,6 +935,7 @@ def run_ours(args) -> dict:
                                f"decode iterations sampled evenly over {sched.n_iters}",
                    "layers": L, "hq": wl.hq, "hkv": wl.hkv, "hq_local": hq, "hkv_local": hkv, "head_dim": D,
                    "page_size": args.page_size, "parallelism": par, "cuda_graph": True,
+                   "graph_warmup": "every distinct captured graph of the timed steps is replayed once, untimed, after the W warm-up steps",
                    "decode_step": ("per layer ONE launch: qk-norm + RoPE + KV append + attention (b200_attn_decode_fused)"
                                    if runner.fuse_pre_attention else "per layer: qk-norm+RoPE launch, attention(+append) launch"),
                    "allreduce": {"b200": "captured: one-shot NVLink push all-reduce of [bs,%d] bf16 fused with residual add + RMSNorm "
