@@ -95,7 +95,7 @@ B200_API int b200_index_rows(const void* weights, int64_t weight_row_stride_byte
  *     and the per-head q/k norm at M/layers/attention.py:50-53.
  *     x viewed as [rows, heads, dim]: element (r,h,i) at x + r*x_row_stride + h*x_head_stride + i
  *     (strides in elements); plain 2-D input uses heads = 1.  out may alias x (in place).
- *     y = float(x) * rsqrt(mean(x^2) + eps) * float(w), one rounding.  dim % 8 == 0, dim <= 16384.
+ *     y = float(x) * rsqrt(mean(x^2) + eps) * float(w), one rounding.  dim % 8 == 0, dim <= 8192.
  * ------------------------------------------------------------------------------------- */
 B200_API int b200_rmsnorm(void* out, const void* x, const void* weight, int64_t rows, int heads, int dim,
                  int64_t x_row_stride, int64_t x_head_stride, int64_t out_row_stride,

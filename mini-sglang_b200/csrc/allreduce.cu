@@ -116,7 +116,7 @@ __device__ __forceinline__ float block_sum(float v, float* red /* [33] */) {
 }
 
 template <typename T, int kIter, bool kNorm>
-__global__ void __launch_bounds__(1024) allreduce_push_kernel(const Params<T> p) {
+__global__ void __launch_bounds__(512) allreduce_push_kernel(const Params<T> p) {
   __shared__ float red[33];
   __shared__ uint32_t s_epoch;
   const int b = blockIdx.x, grid = gridDim.x, tid = threadIdx.x;
@@ -176,21 +176,35 @@ __global__ void __launch_bounds__(1024) allreduce_push_kernel(const Params<T> p)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
         const size_t off = parity_off + ((size_t)r * p.dim + c * 8) * sizeof(T);
-        for (int s = 0; s < p.world; ++s) {
-          uint8_t* slot = mine + off + (size_t)s * p.slot_bytes;
-          Vec8 v = ld_volatile16(slot);
-          uint32_t spins = 0;
-          while (has_sentinel(v)) {
-            if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > 8000000000ull) __trap();  // 8 s: a peer died
-            v = ld_volatile16(slot);
-          }
-          Vec8 arm;
-          arm.w[0] = arm.w[1] = arm.w[2] = arm.w[3] = kSentinel2;
-          *reinterpret_cast<Vec8*>(slot) = arm;  // ready for the launch after next
-          float g[8];
-          unpack8<T>(v, g);
+        // all senders' chunks are requested at once (one L2 round trip instead of `world` dependent ones);
+        // only the ones that have not landed yet are polled again
+        Vec8 v[kMaxWorld];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += g[i];
+        for (int s = 0; s < kMaxWorld; ++s)
+          if (s < p.world) v[s] = ld_volatile16(mine + off + (size_t)s * p.slot_bytes);
+        uint32_t spins = 0;
+        for (;;) {
+          bool missing = false;
+#pragma unroll
+          for (int s = 0; s < kMaxWorld; ++s)
+            if (s < p.world && has_sentinel(v[s])) {
+              v[s] = ld_volatile16(mine + off + (size_t)s * p.slot_bytes);
+              missing = true;
+            }
+          if (!missing) break;
+          if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > 8000000000ull) __trap();  // 8 s: a peer died
+        }
+        Vec8 arm;
+        arm.w[0] = arm.w[1] = arm.w[2] = arm.w[3] = kSentinel2;
+#pragma unroll
+        for (int s = 0; s < kMaxWorld; ++s) {  // rank order: identical bits on every rank
+          if (s < p.world) {
+            *reinterpret_cast<Vec8*>(mine + off + (size_t)s * p.slot_bytes) = arm;  // ready for the launch after next
+            float g[8];
+            unpack8<T>(v[s], g);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += g[i];
+          }
         }
         // y = the all-reduced tensor, rounded once to the 16-bit type like the reference's result
         const Vec8 y = pack8<T>(acc);
@@ -256,7 +270,7 @@ static int launch(const Comm* c, const void* x, int64_t x_rs, void* out, int64_t
   if (threads > 1024) threads = 1024;
   if (chunks > 512) threads = (int)ceil_div(ceil_div(chunks, 2), 32) * 32;
   const int iters = ceil_div(chunks, threads);
-  B200_CHECK_ARG(iters <= 2, "allreduce: dim %d too large (max 16384)", dim);
+  B200_CHECK_ARG(iters <= 2 && threads <= 512, "allreduce: dim %d too large (max 8192)", dim);
   const int grid = rows < kMaxCtas ? (int)rows : kMaxCtas;
   const bool norm = residual != nullptr;
 #define L(IT_, N_) B200_CHECK_CUDA(launch_pdl(allreduce_push_kernel<T, IT_, N_>, dim3(grid), dim3(threads), 0, st, p))
