@@ -48,7 +48,7 @@ def test_prefill_batches_respect_the_token_budget():
         for b in batches:
             assert 0 < sum(d - c for (_, c, d) in b) <= wl.max_extend
             for (t, c, d) in b:
-                start = min(wl.shared_prefix, (s.in_lens[t] - 1) // 64 * 64) if wl.shared_prefix else 0
+                start = min(wl.shared_prefix, (s.in_lens[t] - 1) // 64 * 64, (s.in_lens[0] - 1) // 64 * 64) if wl.shared_prefix else 0
                 assert c == covered.get(t, start) and c < d <= s.in_lens[t]
                 covered[t] = d
         assert covered == {t: n for t, n in enumerate(s.in_lens)}
