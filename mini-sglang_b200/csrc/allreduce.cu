@@ -127,6 +127,13 @@ __global__ void __launch_bounds__(512) allreduce_push_kernel(const Params<T> p) 
   // previous all-reduce, complete by transitivity); the successor may begin its own prologue right away
   pdl_wait();
   pdl_launch_dependents();
+  // the first row's chunks of x are requested before the epoch is read: the two global round trips overlap
+  Vec8 x0[kIter];
+#pragma unroll
+  for (int it = 0; it < kIter; ++it) {
+    const int c = tid + it * blockDim.x;
+    if (b < p.rows && c < chunks) x0[it] = *reinterpret_cast<const Vec8*>(p.x + (int64_t)b * p.x_rs + c * 8);
+  }
   if (tid == 0) {
     // epoch of this launch = stored epoch + 1 (acquire: the count-in below cannot overtake this read)
     uint32_t e;
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(512) allreduce_push_kernel(const Params<T> p) 
     for (int it = 0; it < kIter; ++it) {
       const int c = tid + it * blockDim.x;
       if (c < chunks) {
-        const Vec8 v = without_negative_zero(*reinterpret_cast<const Vec8*>(p.x + (int64_t)r * p.x_rs + c * 8));
+        const Vec8 v = without_negative_zero(r == b ? x0[it] : *reinterpret_cast<const Vec8*>(p.x + (int64_t)r * p.x_rs + c * 8));
         const size_t off = parity_off + (size_t)p.rank * p.slot_bytes + ((size_t)r * p.dim + c * 8) * sizeof(T);
         for (int i = 1; i <= p.world; ++i) {
           const int t = (p.rank + i) % p.world;
