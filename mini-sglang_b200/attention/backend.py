@@ -20,6 +20,7 @@ fused into the attention launch.
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -29,8 +30,6 @@ from .. import _cabi
 from ..core import get_global_ctx
 from ..utils import div_even, get_tp_info
 from .base import BaseAttnBackend, BaseAttnMetadata
-
-import os
 
 _DEBUG_CHECKS = os.environ.get("B200_DEBUG_CHECKS", "0") not in ("", "0")
 _PLAN_HEADER = 4
