@@ -720,29 +720,58 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {
           __threadfence();  // acquire the other chunks' partials
+          // The merge is pure latency (partials sit in L2, written by other SMs): every load whose address
+          // is known is issued before anything is consumed -- (m, l) of all G heads at once, then the
+          // partial outputs kMergeBatch chunks x G heads at a time.
           const int64_t b0 = ((int64_t)u.r * kMaxSplits) * p.hq + u.h * G;
-          for (int g = 0; g < G; ++g) {
-            // lane c holds (m, l) of chunk c
-            float mc = -INFINITY, lc = 0.f;
+          float mc[G], lc[G];
+#pragma unroll
+          for (int g = 0; g < G; ++g) {  // lane c holds (m, l) of chunk c
+            mc[g] = -INFINITY;
+            lc[g] = 0.f;
             if (lane < u.n_chunks) {
               const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml + (b0 + (int64_t)lane * p.hq + g) * 2));
-              mc = ml.x;
-              lc = ml.y;
+              mc[g] = ml.x;
+              lc[g] = ml.y;
             }
-            const float mx = warp_max(mc);
-            const float wc = lane < u.n_chunks ? fast_exp2(mc - mx) : 0.f;
-            const float inv = 1.f / warp_sum(wc * lc);
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int c = 0; c < u.n_chunks; ++c) {
-              const float w = __shfl_sync(0xffffffffu, wc, c);
-              const float4 po = __ldcg(reinterpret_cast<const float4*>(p.part_o + (b0 + (int64_t)c * p.hq + g) * kD) + lane);
-              o.x += w * po.x;
-              o.y += w * po.y;
-              o.z += w * po.z;
-              o.w += w * po.w;
+          }
+          constexpr int kMergeBatch = G <= 2 ? 8 : (G <= 4 ? 4 : 2);
+          float4 o[G];
+          float wc[G], inv[G];
+#pragma unroll
+          for (int g = 0; g < G; ++g) o[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c0 = 0; c0 < u.n_chunks; c0 += kMergeBatch) {
+            float4 po[G][kMergeBatch];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+              for (int j = 0; j < kMergeBatch; ++j)
+                po[g][j] = c0 + j < u.n_chunks
+                               ? __ldcg(reinterpret_cast<const float4*>(p.part_o + (b0 + (int64_t)(c0 + j) * p.hq + g) * kD) + lane)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 == 0) {
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                const float mx = warp_max(mc[g]);
+                wc[g] = lane < u.n_chunks ? fast_exp2(mc[g] - mx) : 0.f;
+                inv[g] = 1.f / warp_sum(wc[g] * lc[g]);
+              }
             }
-            typename DTypeTraits<T>::T2 lo = DTypeTraits<T>::from_float2(o.x * inv, o.y * inv);
-            typename DTypeTraits<T>::T2 hi = DTypeTraits<T>::from_float2(o.z * inv, o.w * inv);
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+              for (int j = 0; j < kMergeBatch; ++j) {  // chunk order 0, 1, ... as in combine.cuh
+                const float w = __shfl_sync(0xffffffffu, wc[g], (c0 + j) & 31);
+                o[g].x += w * po[g][j].x;
+                o[g].y += w * po[g][j].y;
+                o[g].z += w * po[g][j].z;
+                o[g].w += w * po[g][j].w;
+              }
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            typename DTypeTraits<T>::T2 lo = DTypeTraits<T>::from_float2(o[g].x * inv[g], o[g].y * inv[g]);
+            typename DTypeTraits<T>::T2 hi = DTypeTraits<T>::from_float2(o[g].z * inv[g], o[g].w * inv[g]);
             uint2 pk;
             pk.x = *reinterpret_cast<uint32_t*>(&lo);
             pk.y = *reinterpret_cast<uint32_t*>(&hi);
