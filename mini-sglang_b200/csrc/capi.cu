@@ -35,9 +35,11 @@ std::atomic<int> g_decode_lookahead{4};
 // round trip plus the combine pass, so it only pays when whole requests cannot fill the grid.
 std::atomic<int> g_decode_plan_target{2};    // when splitting, aim at target * CTA-hint / kv_heads (request, chunk) items
 std::atomic<int> g_decode_plan_nosplit{75};  // no split once bs * kv_heads * 100 >= nosplit * CTA-hint (0 = always split)
-// 0 = separate combine launch, 1 = the last-arriving CTA merges the partials in the decode launch,
-// 2 = auto: in-kernel (and no combine launch at all) exactly when the policy above does not split.
-std::atomic<int> g_decode_fused_combine{2};
+// 0 = separate combine launch, 1 = the last-arriving chunk's CTA merges the partials in the decode launch (no
+// combine launch at all), 2 = in-kernel exactly when the policy above does not split.  Measured in captured
+// graphs (profiles/r02_decode_merge_sweep.json, after the merge's loads were batched): 1 is faster or equal at every
+// batch / head shape but one (bs 4, hq 8: 11.1 vs 10.6 us); tp4 shard 164.8 k -> 170.1 k tok/s, tp8 shard 233 k -> 252 k.
+std::atomic<int> g_decode_fused_combine{1};
 std::atomic<int> g_decode_early_kv{1};  // captured decode launches stream K/V without waiting for the predecessor
 std::atomic<int> g_decode_defer{1};  // unit epilogue deferred behind the next unit's first tile
 }

@@ -59,8 +59,11 @@ def ref_paged_attention(
     slot_rows: Sequence[torch.Tensor],  # per request: int tensor [kv_len] of slots
     q_lens: Sequence[int],
     scale: float | None = None,
+    exact: bool = False,
 ) -> torch.Tensor:
-    """Ragged batch. Query rows are the concatenation over requests (scheduler.py:236-259)."""
+    """Ragged batch. Query rows are the concatenation over requests (scheduler.py:236-259).
+    `exact`: return the unrounded fp32 result (what oracle/tolerance.vs_exact_oracle expects) instead of
+    rounding it once to q's dtype like a backend does."""
     nnz, hq, d = q.shape
     scale = d**-0.5 if scale is None else scale
     out = torch.empty((nnz, hq, d), dtype=torch.float32)
@@ -71,7 +74,7 @@ def ref_paged_attention(
         out[off : off + ql] = o
         off += ql
     assert off == nnz
-    return out.to(q.dtype)
+    return out if exact else out.to(q.dtype)
 
 
 def ref_backend_forward(

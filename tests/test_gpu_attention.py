@@ -12,19 +12,20 @@ from oracle import metadata as o_meta
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 0, 2, 3], ids=["tcgen05", "cpasync", "tcgen05-inorder", "tcgen05-merge-in-kernel"])
+@pytest.fixture(params=[1, 0, 2, 3], ids=["tcgen05", "cpasync", "tcgen05-inorder-combine-launch", "tcgen05-combine-auto"])
 def decode_impl(request, b200, native_lib):
     """Both decode kernels are held to the same oracle: the tcgen05 + TMA product kernel (with the
     unit epilogue deferred behind the next unit's first tile -- the default -- and strictly in
-    order; with the split-KV merge as its own launch and done by the last-arriving chunk inside
-    the decode launch) and the cp.async / CUDA-core bring-up kernel (selected with the debug options)."""
+    order; with the split-KV merge done by the last-arriving chunk inside the decode launch -- the
+    default --, as its own launch, and under the "in kernel only when nothing is split" policy) and the
+    cp.async / CUDA-core bring-up kernel (selected with the debug options)."""
     impl = 0 if request.param == 0 else 1
     try:
         prev = b200._cabi.set_option("decode_impl", impl)
     except b200._cabi.B200NativeError:
         pytest.skip("cross-check kernel not in this build (B200_BUILD_BRINGUP=1)")
     prev_defer = b200._cabi.set_option("decode_defer_epilogue", 0 if request.param == 2 else 1)
-    prev_merge = b200._cabi.set_option("decode_fused_combine", {3: 1, 2: 0}.get(request.param, 2))
+    prev_merge = b200._cabi.set_option("decode_fused_combine", {3: 2, 2: 0}.get(request.param, 1))
     yield impl
     b200._cabi.set_option("decode_impl", prev)
     b200._cabi.set_option("decode_defer_epilogue", prev_defer)

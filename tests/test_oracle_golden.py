@@ -193,3 +193,52 @@ def test_norm_oracle_matches_flashinfer():
     assert torch.equal(gr.view(torch.int16), _bf16(FI["fused_res_out"]).view(torch.int16))  # residual: exact
     wx = _bf16(FI["fused_x_out"])
     assert ((gx.float() - wx.float()).abs() <= 2.0**-7 * wx.float().abs() + 1e-6).all()
+
+
+def test_tolerance_criteria_on_an_emulated_16bit_p_kernel():
+    """oracle/tolerance.py on a CPU emulation of what every tensor-core backend does (online softmax over
+    128-key tiles, P rounded to bf16 before PV, l from the unrounded P, one bf16 output rounding): inside the
+    2e-3 budget and inside the element-wise 16-bit-P bound; a result that is wrong by 1 % of one V row is not."""
+    from oracle import tolerance
+
+    g = torch.Generator().manual_seed(3)
+    hq, hkv, d = 8, 2, 128
+    lens = [1, 2, 5, 17, 128, 129, 400, 1000]
+    n_slots = sum(lens)
+    kc = torch.randn((n_slots, hkv, d), generator=g).to(torch.bfloat16)
+    vc = torch.randn((n_slots, hkv, d), generator=g).to(torch.bfloat16)
+    q = torch.randn((len(lens), hq, d), generator=g).to(torch.bfloat16)
+    rows, off = [], 0
+    for n in lens:
+        rows.append(torch.arange(off, off + n))
+        off += n
+    ref = o_attn.ref_paged_attention(q, kc, vc, rows, [1] * len(lens), exact=True)
+    assert ref.dtype == torch.float32
+    rounded = o_attn.ref_paged_attention(q, kc, vc, rows, [1] * len(lens))
+    assert rounded.dtype == torch.bfloat16 and torch.equal(rounded, ref.to(torch.bfloat16))
+    absref = o_attn.ref_paged_attention(q, kc, vc.abs(), rows, [1] * len(lens), exact=True)
+    outs = []
+    for i, r in enumerate(rows):
+        kk = kc[r].float().repeat_interleave(hq // hkv, dim=1)
+        vv = vc[r].float().repeat_interleave(hq // hkv, dim=1)
+        s = torch.einsum("hd,nhd->hn", q[i].float(), kk) * (d**-0.5) * 1.4426950408889634
+        m = torch.full((hq,), -float("inf"))
+        l = torch.zeros(hq)
+        o = torch.zeros(hq, d)
+        for t0 in range(0, len(r), 128):
+            st = s[:, t0 : t0 + 128]
+            mn = torch.maximum(m, st.max(dim=1).values)
+            alpha = torch.where(torch.isinf(m), torch.zeros_like(m), torch.exp2(m - mn))
+            p = torch.exp2(st - mn[:, None])
+            l = l * alpha + p.sum(1)
+            o = o * alpha[:, None] + torch.einsum("hn,nhd->hd", p.to(torch.bfloat16).float(), vv[t0 : t0 + 128])
+            m = mn
+        outs.append((o / l[:, None]).to(torch.bfloat16))
+    out = torch.stack(outs)
+    assert tolerance.vs_exact_oracle(out, ref) <= tolerance.ORACLE_REL_TOL
+    assert tolerance.p16_bound_excess(out, ref, absref) <= tolerance.P16_EXCESS_TOL
+    assert tolerance.vs_exact_oracle(rounded, ref) == 0.0  # the exact result, rounded once: nothing beyond half an ulp
+    bad = out.clone()
+    bad[4] = (out[4].float() + 0.01 * vc[rows[4][0], 0].float()).to(torch.bfloat16)
+    assert tolerance.p16_bound_excess(bad, ref, absref) > tolerance.P16_EXCESS_TOL
+    assert tolerance.vs_exact_oracle(bad, ref) > tolerance.ORACLE_REL_TOL
