@@ -50,9 +50,9 @@ B200_API int b200_device_supported(void);
  *   "prefill_full_row": 1 = tcgen05 prefill with one softmax thread per query row (8 warps, whole score row in
  *       registers, setmaxnreg); 0 (default, measured faster) = two threads per row (16 warps).
  *   "decode_lookahead": S^T buffers the UMMA issuer may run ahead (2..4, default 4).
- *   "decode_fused_combine": 0 = separate combine launch, 1 = merge split-KV partials inside the decode
- *       launch, 2 = auto (default): in-kernel, and no combine launch, exactly when the plan policy
- *       leaves the batch unsplit.
+ *   "decode_fused_combine": 1 (default) = the chunk that arrives last merges the split-KV partials inside
+ *       the decode launch (no combine launch), 0 = separate combine launch, 2 = in-kernel exactly when the
+ *       plan policy leaves the batch unsplit (round 1's policy).
  *   "decode_defer_epilogue": 1 (default) = a decode unit's epilogue runs after the next unit's first
  *       tile has been handed to the tensor core; 0 = strictly unit after unit.
  *   "decode_early_kv": 1 (default) = a decode launch that is being captured into a CUDA graph lets its TMA

@@ -10,3 +10,4 @@ timeout 900 python bench.py --config cfg2 --steps 20 --warmup 3 --prefill-batche
 timeout 900 python bench.py --config cfg4 --steps 20 --warmup 3 --prefill-batches 4 --prefill-layers 8 > $O/bench_cfg4.json 2> $O/bench_cfg4.err; echo "bench cfg4 rc=$?"; cut -c1-200 $O/bench_cfg4.json
 timeout 300 python tools/elementwise_bench.py --out $O/elementwise.json > $O/elementwise.log 2>&1; tail -8 $O/elementwise.log
 for n in 2 4 8; do timeout 600 python bench.py --tp-shard $n --steps 40 --warmup 4 --skip-prefill --skip-cpu --skip-ref-gpu > $O/bench_shard$n.json 2> $O/bench_shard$n.err; cut -c1-160 $O/bench_shard$n.json; done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 600 --csv --log-file $O/launches_bench.csv python bench.py --steps 8 --warmup 3 --skip-prefill --skip-cpu --skip-ref-gpu > /dev/null 2>&1; echo "ncu launches rc=$?"
