@@ -11,7 +11,8 @@ graphs) run the sm_100a push kernel of ``csrc/allreduce.cu``; larger messages (p
 north_star keeps it.
 
 Set-up uses ``torch.distributed`` only to exchange the 64-byte CUDA IPC handles of the per-rank
-regions; the data path is hand-written (peer stores + system-scope flags).
+regions; the data path is hand-written (16-byte peer stores over NVLink; the payload is its own
+arrival flag, see csrc/allreduce.cu).
 """
 
 from __future__ import annotations
