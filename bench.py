@@ -23,6 +23,7 @@ its arithmetic is CUDA-only FlashInfer) on the same workload.
 from __future__ import annotations
 
 import argparse
+import gc
 import importlib
 import json
 import os
@@ -785,6 +786,14 @@ def run_ours(args) -> dict:
         if st[0].padded_size not in seen_bs:
             seen_bs.add(st[0].padded_size)
             runner.decode_step(st)
+    # Python's cyclic collector is parked for the timed legs, as serving engines do after warm-up (gc.freeze):
+    # a full collection of a process with torch loaded takes 30-60 ms, and the scheduler thread of this path is
+    # at most 4 steps (the pinned request ring) ahead of the GPU -- at 0.5 ms per step (one rank's shard of tp8) a
+    # single collection inside the timed region tripled the step time (gpurun_out/r2final/bench_shard8.json).
+    if os.environ.get("B200_BENCH_KEEP_GC", "0") == "0":  # =1: A/B of the claim above
+        gc.collect()
+        gc.freeze()
+        gc.disable()
     barrier()
     for k in runner.host_us:
         runner.host_us[k] = 0
@@ -795,14 +804,21 @@ def run_ours(args) -> dict:
         with torch.cuda.stream(runner.stream):
             ev0.record()
         host_t0 = time.perf_counter()
+        step_evs = []
+        step_own_ms = []  # host time of each step minus the time it waited for the GPU (request-info ring)
         for st in steps:
+            t_s, w_s = time.perf_counter(), runner.backend.ring_wait_s
             tokens += runner.decode_step(st)
+            step_own_ms.append(((time.perf_counter() - t_s) - (runner.backend.ring_wait_s - w_s)) * 1e3)
+            step_evs.append(torch.cuda.Event(enable_timing=True))
+            step_evs[-1].record(runner.stream)
         value_host_ms = (time.perf_counter() - host_t0) * 1e3
         host_breakdown = {k: round(v / max(runner.host_us["steps"], 1), 1) for k, v in runner.host_us.items() if k != "steps"}
         with torch.cuda.stream(runner.stream):
             ev1.record()
         barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1), "value_ms")
+    step_gpu_ms = [a.elapsed_time(b) for a, b in zip([ev0] + step_evs[:-1], step_evs)]
     eager_launches = lib.b200_launch_count() - launches0
     graph_launches = sum(runner.graph_launches[runner.pad_bs(len(tr))] for tr in step_triples)
     value = tokens / (ms * 1e-3)
@@ -841,6 +857,7 @@ def run_ours(args) -> dict:
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), "e2e_ms")
     e2e_value = tokens / (e2e_ms * 1e-3)
+    gc.enable()
 
     # ---------------- roofline of the dominant kernel (decode attention): for every timed step an
     # attention-only CUDA graph (L launches, one per layer, each on its own pool slice => L2 cold)
@@ -971,7 +988,13 @@ def run_ours(args) -> dict:
         "metric": f"decode tokens/sec (attention hot path, {L} layers) + prefill TFLOPS, {wl.num_seqs}-seq {wl.model} batch",
         "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 4), "host_enqueue_ms_per_step": round(value_host_ms / args.steps, 4),
-        "host_us_per_step": host_breakdown, "host_us_per_step_gpu_idle": host_unloaded, "timed_ms_by_rank": by_rank or None,
+        "host_us_per_step": host_breakdown, "host_us_per_step_gpu_idle": host_unloaded,
+        # host time of a timed step NOT spent waiting for the GPU: a spike here is a host-side stall (scheduling, GC)
+        "host_step_own_ms": {"median": round(float(np.median(step_own_ms)), 3), "max": round(max(step_own_ms), 3),
+                             "argmax": int(np.argmax(step_own_ms))},
+        "gpu_step_ms": {"median": round(float(np.median(step_gpu_ms)), 3), "max": round(max(step_gpu_ms), 3),
+                        "argmax": int(np.argmax(step_gpu_ms))},
+        "timed_ms_by_rank": by_rank or None,
         "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{wl.name}: {wl.model} attention path, {wl.desc}, "

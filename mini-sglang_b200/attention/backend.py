@@ -21,6 +21,7 @@ fused into the attention launch.
 from __future__ import annotations
 
 import os
+import time
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -139,6 +140,7 @@ class B200AttnBackend(BaseAttnBackend):
         self._info_ring: List[tuple] = []  # (pinned int32 tensor, event of its last copy, numpy view)
         self._layouts: dict = {}
         self._info_next = 0
+        self.ring_wait_s = 0.0  # host time spent waiting for a free request-info buffer (GPU back-pressure)
         self._lib = None
         self._sm_count = 0
         if torch.device(self.device).type == "cuda":
@@ -185,7 +187,9 @@ class B200AttnBackend(BaseAttnBackend):
         else:
             slot = self._info_next
             self._info_next = (slot + 1) % self._INFO_RING
+            t0 = time.perf_counter()
             self._info_ring[slot][1].synchronize()  # the kernels launched 4 batches ago: long done
+            self.ring_wait_s += time.perf_counter() - t0
             if self._info_ring[slot][0].numel() < n:
                 host = torch.empty(n, dtype=torch.int32, pin_memory=True)
                 self._info_ring[slot] = (host, self._info_ring[slot][1], host.numpy())
