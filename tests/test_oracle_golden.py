@@ -217,28 +217,38 @@ def test_tolerance_criteria_on_an_emulated_16bit_p_kernel():
     rounded = o_attn.ref_paged_attention(q, kc, vc, rows, [1] * len(lens))
     assert rounded.dtype == torch.bfloat16 and torch.equal(rounded, ref.to(torch.bfloat16))
     absref = o_attn.ref_paged_attention(q, kc, vc.abs(), rows, [1] * len(lens), exact=True)
-    outs = []
-    for i, r in enumerate(rows):
+    def emulate(tile):
+        outs = []
+        for i, r in enumerate(rows):
+            outs.append(emulate_one(i, r, tile))
+        return torch.stack(outs)
+
+    def emulate_one(i, r, tile):
         kk = kc[r].float().repeat_interleave(hq // hkv, dim=1)
         vv = vc[r].float().repeat_interleave(hq // hkv, dim=1)
         s = torch.einsum("hd,nhd->hn", q[i].float(), kk) * (d**-0.5) * 1.4426950408889634
         m = torch.full((hq,), -float("inf"))
         l = torch.zeros(hq)
         o = torch.zeros(hq, d)
-        for t0 in range(0, len(r), 128):
-            st = s[:, t0 : t0 + 128]
+        for t0 in range(0, len(r), tile):
+            st = s[:, t0 : t0 + tile]
             mn = torch.maximum(m, st.max(dim=1).values)
             alpha = torch.where(torch.isinf(m), torch.zeros_like(m), torch.exp2(m - mn))
             p = torch.exp2(st - mn[:, None])
             l = l * alpha + p.sum(1)
-            o = o * alpha[:, None] + torch.einsum("hn,nhd->hd", p.to(torch.bfloat16).float(), vv[t0 : t0 + 128])
+            o = o * alpha[:, None] + torch.einsum("hn,nhd->hd", p.to(torch.bfloat16).float(), vv[t0 : t0 + tile])
             m = mn
-        outs.append((o / l[:, None]).to(torch.bfloat16))
-    out = torch.stack(outs)
+        return (o / l[:, None]).to(torch.bfloat16)
+
+    out = emulate(128)
     assert tolerance.vs_exact_oracle(out, ref) <= tolerance.ORACLE_REL_TOL
     assert tolerance.p16_bound_excess(out, ref, absref) <= tolerance.P16_EXCESS_TOL
     assert tolerance.vs_exact_oracle(rounded, ref) == 0.0  # the exact result, rounded once: nothing beyond half an ulp
+    # a second kernel with another tile size (different running maxima, different P roundings): the pair bound
+    other = emulate(64)
+    assert tolerance.pair_p16_bound_excess(out, other, absref) <= tolerance.P16_EXCESS_TOL
     bad = out.clone()
     bad[4] = (out[4].float() + 0.01 * vc[rows[4][0], 0].float()).to(torch.bfloat16)
     assert tolerance.p16_bound_excess(bad, ref, absref) > tolerance.P16_EXCESS_TOL
     assert tolerance.vs_exact_oracle(bad, ref) > tolerance.ORACLE_REL_TOL
+    assert tolerance.pair_p16_bound_excess(bad, other, absref) > tolerance.P16_EXCESS_TOL
