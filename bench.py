@@ -504,6 +504,12 @@ class AttentionPathRunner:
                     torch.distributed.all_reduce(self.hidden[:bs], group=self.tp_group)
             if host_copy:
                 out_h[:bs].copy_(self.last_out[bs].view(bs, -1), non_blocking=True)
+            # The step is over for the scheduler: its metadata dies with it, as in the engine, where a Batch does not
+            # outlive its forward.  The timed steps are scheduled ahead of the timed region here; left alive, their
+            # metadata (slot-table snapshot, 1-2 MB each) made the caching allocator cudaMalloc a fresh segment every
+            # ~10 steps INSIDE the timed region: 0.3 ms as a rule, 5 ms .. 65 ms when the driver was busy (step 15 of
+            # every run, profiles/r02_stall_probe.txt) -- with 0.5 ms steps (one rank's shard of tp8) that was the run.
+            batch.attn_metadata = None
         return n_tokens
 
 
@@ -807,10 +813,10 @@ def run_ours(args) -> dict:
         if st[0].padded_size not in seen_bs:
             seen_bs.add(st[0].padded_size)
             runner.decode_step(st)
-    # Python's cyclic collector is parked for the timed legs, as serving engines do after warm-up (gc.freeze):
-    # a full collection of a process with torch loaded takes 30-60 ms, and the scheduler thread of this path is
-    # at most 4 steps (the pinned request ring) ahead of the GPU -- at 0.5 ms per step (one rank's shard of tp8) a
-    # single collection inside the timed region tripled the step time (gpurun_out/r2final/bench_shard8.json).
+    # Python's cyclic collector is parked for the timed legs, as serving engines do after warm-up (gc.freeze): a
+    # full collection of a process with torch loaded takes 30-60 ms and the scheduler thread of this path is at
+    # most 4 steps (the pinned request ring) ahead of the GPU.  (Not what stalled the short-step runs of round 2 --
+    # that was cudaMalloc, see decode_step -- profiles/r02_stall_probe.txt has the A/B.)
     if os.environ.get("B200_BENCH_KEEP_GC", "0") == "0":  # =1: A/B of the claim above
         gc.collect()
         gc.freeze()
