@@ -461,7 +461,7 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
     const int ct = tid - 128;          // 0..127 = TMEM lane = key within tile = output dim
     const int cw = warp - 4;           // TMEM lane quadrant of this warp
     const uint32_t lane_base = (uint32_t)(cw * 32) << 16;
-    float* red_max = red;              // [2][4][16], by tile parity
+    float* red_max = red;              // [2][16 heads][4 warps], by tile parity
     uint32_t tile_count = 0, fin_count = 0, unit_par = 0, epi_fin = 0;
     // State of one unit's online softmax; everything the epilogue needs.
     struct UnitState {
@@ -652,15 +652,16 @@ attn_decode_tc_kernel(const Params<T> p, const __grid_constant__ CUtensorMap map
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           sv[g] = valid ? __uint_as_float(s[g]) * p.scale_log2 : -INFINITY;
-          const float mx = warp_max(sv[g]);
-          if (lane == 0) rm[cw * 16 + g] = mx;
+          const float mx = warp_max_redux(sv[g]);
+          if (lane == 0) rm[g * 4 + cw] = mx;  // [head][warp]: the four warp maxima of a head are one 16-byte read
         }
         named_bar_sync(1, 128);
         float alpha[G];
         uint8_t* pdst = smem + Smem::pbuf + (tc & 1) * kPBufBytes;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const float mt = fmaxf(fmaxf(rm[g], rm[16 + g]), fmaxf(rm[32 + g], rm[48 + g]));
+          const float4 wm = *reinterpret_cast<const float4*>(rm + g * 4);
+          const float mt = fmaxf(fmaxf(wm.x, wm.y), fmaxf(wm.z, wm.w));
           const float m_new = fmaxf(cur.m_run[g], mt);  // finite: every tile has >= 1 valid key
           alpha[g] = fast_exp2(cur.m_run[g] - m_new);
           const float pv = fast_exp2(sv[g] - m_new);

@@ -89,6 +89,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       "l"(m), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// Warp-wide fp32 maximum in ONE instruction (sm_100a: redux.sync on f32, SASS CREDUX.MAX.F32) instead of five
+// shuffle + max rounds; same value as common.cuh::warp_max (a maximum does not depend on the order).
+__device__ __forceinline__ float warp_max_redux(float x) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // gather4: four arbitrary rows (r0..r3) x one box of columns starting at c0 -> 4 consecutive
 // smem rows.  Rows outside the tensor are zero-filled (and still counted in complete_tx).
 __device__ __forceinline__ void tma_gather4(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar,
