@@ -14,7 +14,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "mini-sglang_b200" / "libb200attn.so"
 WATCH = ["UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UTMAPF", "LDTM", "STTM", "HMMA", "LDGSTS", "SYNCS", "MUFU.EX2",
-         "USETMAXREG", "ACQBULK", "LDG", "STG", "LDS", "STS", "RED", "ATOM", "BAR", "FFMA", "SHFL"]
+         "USETMAXREG", "ACQBULK", "CREDUX", "LDG", "STG", "LDS", "STS", "RED", "ATOM", "BAR", "FFMA", "SHFL"]
 
 
 def main():
